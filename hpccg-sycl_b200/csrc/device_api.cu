@@ -1,0 +1,1060 @@
+// device_api.cu -- hpccg_dev_* entry points of include/hpccg_b200.h: the ELL device mirror, the kernel
+// launchers and the device-resident CG loop.  There is NO CPU fallback in this file: every operation is
+// a CUDA kernel launch, and every CUDA error is returned to the caller.
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.hpp"
+#include "context.hpp"
+#include "device_matrix.hpp"
+#include "kernels.cuh"
+
+namespace hpccg {
+
+// ---- error state -------------------------------------------------------------------------------------
+static thread_local std::string t_error;
+std::atomic<long long> g_launch_count{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+const char *last_error() { return t_error.c_str(); }
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_error = buf;
+  return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[1024];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  t_error = buf;
+  return (int)e;
+}
+
+// ---- device info ---------------------------------------------------------------------------------------
+static Device g_dev;
+static std::once_flag g_dev_once;
+
+const Device &device_info() {
+  std::call_once(g_dev_once, [] {
+    int id = 0;
+    if (cudaGetDevice(&id) == cudaSuccess) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) {
+        g_dev.sm_count = prop.multiProcessorCount;
+        g_dev.id = id;
+      }
+    }
+  });
+  return g_dev;
+}
+
+int stream_grid(long long work_items, int blocks_per_sm) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)device_info().sm_count * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks > kMaxPartials) blocks = kMaxPartials;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// A small per-device workspace for the stand-alone reductions (hpccg_dev_dot, max_abs_diff).
+struct GlobalWorkspace {
+  double *partials = nullptr;
+  unsigned *counter = nullptr;
+  std::mutex mu;
+};
+static GlobalWorkspace g_ws[16];
+
+static int global_workspace(GlobalWorkspace **out) {
+  int dev = 0;
+  HPCCG_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(HPCCG_ERR_ARG, "device index %d out of range", dev);
+  GlobalWorkspace &w = g_ws[dev];
+  std::lock_guard<std::mutex> lk(w.mu);
+  if (!w.partials) {
+    HPCCG_CUDA(cudaMalloc(&w.partials, sizeof(double) * kMaxPartials));
+    HPCCG_CUDA(cudaMalloc(&w.counter, sizeof(unsigned)));
+    HPCCG_CUDA(cudaMemset(w.counter, 0, sizeof(unsigned)));
+  }
+  *out = &w;
+  return 0;
+}
+
+int ensure_solver_workspace(hpccg_dev_matrix *m, int max_iter, int nranks) {
+  const long long ncol_pad = round_up(std::max(m->ncol, 2), 512);
+  if (!m->r) {
+    HPCCG_CUDA(cudaMalloc(&m->r, sizeof(double) * m->npad));
+    HPCCG_CUDA(cudaMalloc(&m->Ap, sizeof(double) * m->npad));
+    HPCCG_CUDA(cudaMalloc(&m->p, sizeof(double) * ncol_pad));
+    HPCCG_CUDA(cudaMemset(m->p, 0, sizeof(double) * ncol_pad));
+  }
+  if (m->hist_cap < max_iter + 1) {
+    if (m->hist) HPCCG_CUDA(cudaFree(m->hist));
+    m->hist = nullptr;
+    HPCCG_CUDA(cudaMalloc(&m->hist, sizeof(double) * (max_iter + 1)));
+    m->hist_cap = max_iter + 1;
+  }
+  if (m->gathered_cap < nranks) {
+    if (m->gathered) HPCCG_CUDA(cudaFree(m->gathered));
+    m->gathered = nullptr;
+    HPCCG_CUDA(cudaMalloc(&m->gathered, sizeof(double) * std::max(nranks, 8)));
+    m->gathered_cap = std::max(nranks, 8);
+  }
+  if (!m->comm_stream) {
+    HPCCG_CUDA(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
+    HPCCG_CUDA(cudaEventCreateWithFlags(&m->ev_p_ready, cudaEventDisableTiming));
+    HPCCG_CUDA(cudaEventCreateWithFlags(&m->ev_halo_done, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+int ensure_scratch(hpccg_dev_matrix *m, long long doubles) {
+  if (m->scratch_cap >= doubles) return 0;
+  if (m->scratch_x) HPCCG_CUDA(cudaFree(m->scratch_x));
+  if (m->scratch_y) HPCCG_CUDA(cudaFree(m->scratch_y));
+  m->scratch_x = m->scratch_y = nullptr;
+  m->scratch_cap = 0;
+  HPCCG_CUDA(cudaMalloc(&m->scratch_x, sizeof(double) * doubles));
+  HPCCG_CUDA(cudaMalloc(&m->scratch_y, sizeof(double) * doubles));
+  m->scratch_cap = doubles;
+  return 0;
+}
+
+static int alloc_common(hpccg_dev_matrix *m) {
+  HPCCG_CUDA(cudaGetDevice(&m->device));
+  HPCCG_CUDA(cudaMalloc(&m->vals, sizeof(double) * (size_t)m->slots * m->npad));
+  HPCCG_CUDA(cudaMalloc(&m->cols, sizeof(int) * (size_t)m->slots * m->npad));
+  HPCCG_CUDA(cudaMalloc(&m->partials, sizeof(double) * kMaxPartials));
+  HPCCG_CUDA(cudaMalloc(&m->state, sizeof(CgState)));
+  cg_state_init_kernel<<<1, 32>>>(m->state);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- SpMV launch ----------------------------------------------------------------------------------------
+template <int SLOTS, int RPT, bool DOT>
+static int spmv_occupancy_grid() {
+  static int cached = 0;
+  if (cached) return cached;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_ell_kernel<SLOTS, RPT, DOT>, kThreads, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 2;
+  cached = per_sm * device_info().sm_count;
+  if (cached > kMaxPartials / 4) cached = kMaxPartials / 4;  // room for interior + two boundary launches
+  return cached;
+}
+
+struct SpmvPlan {
+  int row_begin, row_end, tiles, grid;
+};
+
+template <int RPT>
+static SpmvPlan plan_range(int row_begin, int row_end, int max_grid) {
+  SpmvPlan p{row_begin, row_end, 0, 0};
+  if (row_end <= row_begin) return p;
+  const int base = row_begin & ~(RPT - 1);
+  const int tile_rows = kThreads * RPT;
+  p.tiles = (row_end - base + tile_rows - 1) / tile_rows;
+  p.grid = std::min(p.tiles, max_grid);
+  return p;
+}
+
+template <int SLOTS, int RPT, bool DOT>
+static int launch_spmv_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                         int total_partials, const FinishParams &fp, cudaStream_t s) {
+  if (pl.grid == 0) return 0;
+  spmv_ell_kernel<SLOTS, RPT, DOT><<<pl.grid, kThreads, 0, s>>>(m->vals, m->cols, m->npad, m->slots, x, y, pl.row_begin,
+                                                                 pl.row_end, pl.tiles, m->partials, partial_offset,
+                                                                 total_partials, &m->state->counter, fp);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool DOT>
+static int spmv_max_grid(int slots) {
+  if (slots == 27) return spmv_occupancy_grid<27, 2, DOT>();
+  if (slots == 7) return spmv_occupancy_grid<7, 2, DOT>();
+  return spmv_occupancy_grid<0, 2, DOT>();
+}
+
+template <bool DOT>
+static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                       int total_partials, const FinishParams &fp, cudaStream_t s) {
+  if (m->slots == 27) return launch_spmv_t<27, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
+  if (m->slots == 7) return launch_spmv_t<7, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
+  return launch_spmv_t<0, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+
+// Whole-matrix SpMV (+ optional fused x.y) in one launch.
+static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool dot, const FinishParams &fp,
+                     cudaStream_t s) {
+  if (!aligned16(x) || !aligned16(y)) return fail(HPCCG_ERR_ARG, "SpMV vectors must be 16-byte aligned");
+  if (dot) {
+    SpmvPlan pl = plan_range<2>(0, m->n, spmv_max_grid<true>(m->slots));
+    return launch_spmv<true>(m, x, y, pl, 0, pl.grid, fp, s);
+  }
+  SpmvPlan pl = plan_range<2>(0, m->n, spmv_max_grid<false>(m->slots));
+  return launch_spmv<false>(m, x, y, pl, 0, 0, fp, s);
+}
+
+static FinishParams fin_store(double *out) {
+  FinishParams fp{};
+  fp.mode = FIN_STORE;
+  fp.out = out;
+  return fp;
+}
+
+}  // namespace hpccg
+
+using namespace hpccg;
+
+// ================================================================================================
+// C-ABI: library / device
+// ================================================================================================
+extern "C" {
+
+const char *hpccg_last_error(void) { return last_error(); }
+int hpccg_version(void) { return 100; }
+long long hpccg_launch_count(void) { return g_launch_count.load(); }
+
+int hpccg_device_count(int *count) {
+  HPCCG_CUDA(cudaGetDeviceCount(count));
+  return 0;
+}
+int hpccg_set_device(int device) {
+  HPCCG_CUDA(cudaSetDevice(device));
+  return 0;
+}
+int hpccg_device_synchronize(void) {
+  HPCCG_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+int hpccg_dev_malloc(void **ptr, long long bytes) {
+  HPCCG_CUDA(cudaMalloc(ptr, (size_t)std::max<long long>(bytes, 16)));
+  return 0;
+}
+int hpccg_dev_free(void *ptr) {
+  HPCCG_CUDA(cudaFree(ptr));
+  return 0;
+}
+int hpccg_host_malloc_pinned(void **ptr, long long bytes) {
+  HPCCG_CUDA(cudaMallocHost(ptr, (size_t)std::max<long long>(bytes, 16)));
+  return 0;
+}
+int hpccg_host_free_pinned(void *ptr) {
+  HPCCG_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+int hpccg_memcpy_h2d(void *dst, const void *src, long long bytes, void *stream) {
+  HPCCG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int hpccg_memcpy_d2h(void *dst, const void *src, long long bytes, void *stream) {
+  HPCCG_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int hpccg_stream_synchronize(void *stream) {
+  HPCCG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+// ================================================================================================
+// Device matrix
+// ================================================================================================
+int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_row,
+                            const double *const *ptr_to_vals_in_row, const int *const *ptr_to_inds_in_row,
+                            hpccg_dev_matrix **out) {
+  if (!out || local_nrow <= 0 || local_ncol < local_nrow || !nnz_in_row || !ptr_to_vals_in_row || !ptr_to_inds_in_row)
+    return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_create: bad arguments");
+  const int n = local_nrow;
+  // slot count = longest row; first/last rows that touch halo columns bound the interior range
+  const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+  std::vector<int> tmax(nthreads, 0), tfirst(nthreads, n), tlast(nthreads, -1), tbad(nthreads, 0);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        const long long lo = (long long)n * t / nthreads, hi = (long long)n * (t + 1) / nthreads;
+        for (long long i = lo; i < hi; ++i) {
+          const int nnz = nnz_in_row[i];
+          if (nnz > tmax[t]) tmax[t] = nnz;
+          const int *ci = ptr_to_inds_in_row[i];
+          for (int j = 0; j < nnz; ++j) {
+            if (ci[j] < 0 || ci[j] >= local_ncol) tbad[t] = 1;
+            if (ci[j] >= n) {
+              if (i < tfirst[t]) tfirst[t] = (int)i;
+              if (i > tlast[t]) tlast[t] = (int)i;
+            }
+          }
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  int slots = 1;
+  bool bad = false;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    slots = std::max(slots, tmax[t]);
+    bad = bad || tbad[t];
+  }
+  if (bad) return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_create: column index outside [0, local_ncol) -- run make_local_matrix first");
+
+  hpccg_dev_matrix *m = new hpccg_dev_matrix();
+  m->n = n;
+  m->ncol = local_ncol;
+  m->slots = slots;
+  m->npad = round_up(n, 512);
+  // halo-touching rows: leading run [0,a) and trailing run [b,n); a row in the first half extends a,
+  // one in the second half lowers b
+  int a = 0, b = n;
+  {
+    // a second, cheap pass over the per-thread extrema is not enough to split the two runs, so rescan
+    // only when a halo exists at all
+    bool any = false;
+    for (unsigned t = 0; t < nthreads; ++t) any = any || tlast[t] >= 0;
+    if (any) {
+      const int half = n / 2;
+      std::vector<int> ta(nthreads, 0), tb(nthreads, n);
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+          const long long lo = (long long)n * t / nthreads, hi = (long long)n * (t + 1) / nthreads;
+          for (long long i = lo; i < hi; ++i) {
+            const int nnz = nnz_in_row[i];
+            const int *ci = ptr_to_inds_in_row[i];
+            bool ext = false;
+            for (int j = 0; j < nnz; ++j) ext = ext || ci[j] >= n;
+            if (!ext) continue;
+            if (i < half) ta[t] = std::max(ta[t], (int)i + 1);
+            else tb[t] = std::min(tb[t], (int)i);
+          }
+        });
+      for (auto &t : th) t.join();
+      for (unsigned t = 0; t < nthreads; ++t) {
+        a = std::max(a, ta[t]);
+        b = std::min(b, tb[t]);
+      }
+    }
+  }
+  m->interior_begin = a;
+  m->interior_end = std::max(a, b);
+
+  int rc = alloc_common(m);
+  if (rc) {
+    hpccg_dev_matrix_destroy(m);
+    return rc;
+  }
+
+  // Repack rows into column-major ELL through two pinned staging buffers and copy with 2-D memcpys.
+  const int chunk = (int)std::min<long long>(m->npad, 1 << 18);  // rows per staging chunk
+  double *hv[2] = {nullptr, nullptr};
+  int *hc[2] = {nullptr, nullptr};
+  cudaStream_t cs = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  auto cleanup = [&] {
+    for (int i = 0; i < 2; ++i) {
+      if (hv[i]) cudaFreeHost(hv[i]);
+      if (hc[i]) cudaFreeHost(hc[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+    if (cs) cudaStreamDestroy(cs);
+  };
+#define HPCCG_CUDA_CLEAN(call)                                         \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) {                                           \
+      cleanup();                                                       \
+      hpccg_dev_matrix_destroy(m);                                     \
+      return fail_cuda(e_, #call, __FILE__, __LINE__);                 \
+    }                                                                  \
+  } while (0)
+  HPCCG_CUDA_CLEAN(cudaStreamCreate(&cs));
+  for (int i = 0; i < 2; ++i) {
+    HPCCG_CUDA_CLEAN(cudaMallocHost(&hv[i], sizeof(double) * (size_t)slots * chunk));
+    HPCCG_CUDA_CLEAN(cudaMallocHost(&hc[i], sizeof(int) * (size_t)slots * chunk));
+    HPCCG_CUDA_CLEAN(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+  }
+  int buf = 0;
+  for (long long r0 = 0; r0 < m->npad; r0 += chunk, buf ^= 1) {
+    const int rows = (int)std::min<long long>(chunk, m->npad - r0);
+    HPCCG_CUDA_CLEAN(cudaEventSynchronize(ev[buf]));  // staging buffer free again
+    double *sv = hv[buf];
+    int *sc = hc[buf];
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        const int lo = (int)((long long)rows * t / nthreads), hi = (int)((long long)rows * (t + 1) / nthreads);
+        for (int i = lo; i < hi; ++i) {
+          const long long row = r0 + i;
+          int nnz = 0;
+          const double *cv = nullptr;
+          const int *ci = nullptr;
+          if (row < n) {
+            nnz = nnz_in_row[row];
+            cv = ptr_to_vals_in_row[row];
+            ci = ptr_to_inds_in_row[row];
+          }
+          for (int j = 0; j < nnz; ++j) {
+            sv[(size_t)j * chunk + i] = cv[j];
+            sc[(size_t)j * chunk + i] = ci[j];
+          }
+          for (int j = nnz; j < slots; ++j) {
+            sv[(size_t)j * chunk + i] = 0.0;
+            sc[(size_t)j * chunk + i] = -1;
+          }
+        }
+      });
+    for (auto &t : th) t.join();
+    HPCCG_CUDA_CLEAN(cudaMemcpy2DAsync(m->vals + r0, sizeof(double) * m->npad, sv, sizeof(double) * chunk,
+                                       sizeof(double) * rows, slots, cudaMemcpyHostToDevice, cs));
+    HPCCG_CUDA_CLEAN(cudaMemcpy2DAsync(m->cols + r0, sizeof(int) * m->npad, sc, sizeof(int) * chunk, sizeof(int) * rows,
+                                       slots, cudaMemcpyHostToDevice, cs));
+    HPCCG_CUDA_CLEAN(cudaEventRecord(ev[buf], cs));
+  }
+  HPCCG_CUDA_CLEAN(cudaStreamSynchronize(cs));
+#undef HPCCG_CUDA_CLEAN
+  cleanup();
+  *out = m;
+  return 0;
+}
+
+int hpccg_dev_matrix_generate(int nx, int ny, int nz, int rank, int size, int stencil, const int *lower_plane_to_local,
+                              const int *upper_plane_to_local, int local_ncol, hpccg_dev_matrix **out) {
+  if (!out || nx <= 0 || ny <= 0 || nz <= 0 || size <= 0 || rank < 0 || rank >= size || (stencil != 27 && stencil != 7))
+    return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_generate: bad arguments");
+  const long long n = (long long)nx * ny * nz;
+  if (n > 2147483647LL - 1024) return fail(HPCCG_ERR_ARG, "local_nrow %lld does not fit int32", n);
+  const long long plane = (long long)nx * ny;
+  const bool has_lower = rank > 0, has_upper = rank < size - 1;
+  if ((has_lower && !lower_plane_to_local) || (has_upper && !upper_plane_to_local))
+    return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_generate: neighbour plane tables missing");
+  hpccg_dev_matrix *m = new hpccg_dev_matrix();
+  m->n = (int)n;
+  m->ncol = local_ncol;
+  // slot count = longest row of THIS rank's block (27 / 7 for an interior point, fewer for thin blocks)
+  auto span = [](int len, bool lo_open, bool hi_open) {
+    // max number of in-range offsets {-1,0,1} over positions of a 1-D extent
+    int best = 1;
+    for (int i = 0; i < len && i < 3; ++i) {
+      for (int pos : {i, len - 1 - i}) {
+        int c = 1 + ((pos > 0 || lo_open) ? 1 : 0) + ((pos < len - 1 || hi_open) ? 1 : 0);
+        best = std::max(best, c);
+      }
+    }
+    return best;
+  };
+  const int cx = span(nx, false, false), cy = span(ny, false, false), cz = span(nz, has_lower, has_upper);
+  m->slots = stencil == 27 ? cx * cy * cz : 1 + (cx - 1) + (cy - 1) + (cz - 1);
+  m->npad = round_up(n, 512);
+  int a = has_lower ? (int)plane : 0, b = has_upper ? (int)(n - plane) : (int)n;
+  if (a > b) a = b = (int)n;
+  m->interior_begin = a;
+  m->interior_end = b;
+  int rc = alloc_common(m);
+  if (rc) {
+    hpccg_dev_matrix_destroy(m);
+    return rc;
+  }
+  int *d_lower = nullptr, *d_upper = nullptr;
+  auto fail_clean = [&](int code) {
+    if (d_lower) cudaFree(d_lower);
+    if (d_upper) cudaFree(d_upper);
+    hpccg_dev_matrix_destroy(m);
+    return code;
+  };
+  if (has_lower) {
+    cudaError_t e = cudaMalloc(&d_lower, sizeof(int) * plane);
+    if (e == cudaSuccess) e = cudaMemcpy(d_lower, lower_plane_to_local, sizeof(int) * plane, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_clean(fail_cuda(e, "lower plane table", __FILE__, __LINE__));
+  }
+  if (has_upper) {
+    cudaError_t e = cudaMalloc(&d_upper, sizeof(int) * plane);
+    if (e == cudaSuccess) e = cudaMemcpy(d_upper, upper_plane_to_local, sizeof(int) * plane, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail_clean(fail_cuda(e, "upper plane table", __FILE__, __LINE__));
+  }
+  generate_ell_kernel<<<stream_grid(m->npad, 16), kThreads>>>(nx, ny, nz, n * rank, n * size, stencil == 7 ? 1 : 0,
+                                                               m->slots, m->npad, d_lower, d_upper, m->vals, m->cols);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail_clean(fail_cuda(e, "generate_ell_kernel", __FILE__, __LINE__));
+  if (d_lower) cudaFree(d_lower);
+  if (d_upper) cudaFree(d_upper);
+  *out = m;
+  return 0;
+}
+
+int hpccg_dev_matrix_set_halo(hpccg_dev_matrix *m, int num_neighbors, const int *neighbors, const int *recv_length,
+                              const int *send_length, const int *elements_to_send, int total_to_be_sent) {
+  if (!m || num_neighbors < 0 || total_to_be_sent < 0) return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_set_halo: bad arguments");
+  long long recv_total = 0, send_total = 0;
+  for (int i = 0; i < num_neighbors; ++i) {
+    recv_total += recv_length[i];
+    send_total += send_length[i];
+  }
+  if (recv_total != m->ncol - m->n || send_total != total_to_be_sent)
+    return fail(HPCCG_ERR_ARG, "halo plan inconsistent: recv %lld vs %d externals, send %lld vs %d", recv_total,
+                m->ncol - m->n, send_total, total_to_be_sent);
+  m->num_neighbors = num_neighbors;
+  m->neighbors.assign(neighbors, neighbors + num_neighbors);
+  m->recv_length.assign(recv_length, recv_length + num_neighbors);
+  m->send_length.assign(send_length, send_length + num_neighbors);
+  m->total_to_be_sent = total_to_be_sent;
+  if (m->d_elements_to_send) HPCCG_CUDA(cudaFree(m->d_elements_to_send));
+  if (m->d_send_buffer) HPCCG_CUDA(cudaFree(m->d_send_buffer));
+  m->d_elements_to_send = nullptr;
+  m->d_send_buffer = nullptr;
+  if (total_to_be_sent > 0) {
+    for (int i = 0; i < total_to_be_sent; ++i)
+      if (elements_to_send[i] < 0 || elements_to_send[i] >= m->n)
+        return fail(HPCCG_ERR_ARG, "elements_to_send[%d] = %d outside local rows", i, elements_to_send[i]);
+    HPCCG_CUDA(cudaMalloc(&m->d_elements_to_send, sizeof(int) * total_to_be_sent));
+    HPCCG_CUDA(cudaMalloc(&m->d_send_buffer, sizeof(double) * total_to_be_sent));
+    HPCCG_CUDA(cudaMemcpy(m->d_elements_to_send, elements_to_send, sizeof(int) * total_to_be_sent, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
+  if (!m) return 0;
+  cudaFree(m->vals);
+  cudaFree(m->cols);
+  cudaFree(m->d_elements_to_send);
+  cudaFree(m->d_send_buffer);
+  cudaFree(m->partials);
+  cudaFree(m->state);
+  cudaFree(m->gathered);
+  cudaFree(m->r);
+  cudaFree(m->p);
+  cudaFree(m->Ap);
+  cudaFree(m->hist);
+  cudaFree(m->scratch_x);
+  cudaFree(m->scratch_y);
+  if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
+  if (m->ev_p_ready) cudaEventDestroy(m->ev_p_ready);
+  if (m->ev_halo_done) cudaEventDestroy(m->ev_halo_done);
+  delete m;
+  return 0;
+}
+
+int hpccg_dev_matrix_info(const hpccg_dev_matrix *m, int *local_nrow, int *local_ncol, int *slots, long long *padded_rows) {
+  if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (local_nrow) *local_nrow = m->n;
+  if (local_ncol) *local_ncol = m->ncol;
+  if (slots) *slots = m->slots;
+  if (padded_rows) *padded_rows = m->npad;
+  return 0;
+}
+
+int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int *cols_host) {
+  if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (vals_host) HPCCG_CUDA(cudaMemcpy(vals_host, m->vals, sizeof(double) * (size_t)m->slots * m->npad, cudaMemcpyDeviceToHost));
+  if (cols_host) HPCCG_CUDA(cudaMemcpy(cols_host, m->cols, sizeof(int) * (size_t)m->slots * m->npad, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int hpccg_dev_matrix_bytes(const hpccg_dev_matrix *m, long long *bytes) {
+  if (!m || !bytes) return fail(HPCCG_ERR_ARG, "null argument");
+  *bytes = (long long)m->slots * m->npad * 12;
+  return 0;
+}
+
+// ================================================================================================
+// Kernels
+// ================================================================================================
+int hpccg_dev_spmv(const hpccg_dev_matrix *m, const double *x, double *y, void *stream) {
+  if (!m || !x || !y) return fail(HPCCG_ERR_ARG, "hpccg_dev_spmv: null argument");
+  FinishParams fp{};
+  return spmv_full(m, x, y, false, fp, (cudaStream_t)stream);
+}
+
+int hpccg_dev_spmv_dot(const hpccg_dev_matrix *m, const double *x, double *y, double *result_dev, void *stream) {
+  if (!m || !x || !y || !result_dev) return fail(HPCCG_ERR_ARG, "hpccg_dev_spmv_dot: null argument");
+  return spmv_full(m, x, y, true, fin_store(result_dev), (cudaStream_t)stream);
+}
+
+int hpccg_dev_dot(int n, const double *x, const double *y, double *result_dev, void *stream) {
+  if (n < 0 || !x || !y || !result_dev) return fail(HPCCG_ERR_ARG, "hpccg_dev_dot: bad argument");
+  GlobalWorkspace *w = nullptr;
+  HPCCG_TRY(global_workspace(&w));
+  std::lock_guard<std::mutex> lk(w->mu);
+  const int grid = stream_grid((n + 1) / 2);
+  if (x == y)
+    dot_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, x, y, w->partials, grid, w->counter, fin_store(result_dev));
+  else
+    dot_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, x, y, w->partials, grid, w->counter, fin_store(result_dev));
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_waxpby(int n, double alpha, const double *x, double beta, const double *beta_dev, const double *y,
+                         double *w, const CgState *st_check, cudaStream_t s) {
+  if (n == 0) return 0;
+  const int grid = stream_grid((n + 1) / 2);
+  // same branch selection as waxpby.cpp:73,79,85; a device-side beta always takes the alpha==1 form
+  if (alpha == 1.0) waxpby_kernel<0><<<grid, kThreads, 0, s>>>(n, alpha, x, beta, beta_dev, y, w, st_check);
+  else if (beta == 1.0 && !beta_dev) waxpby_kernel<1><<<grid, kThreads, 0, s>>>(n, alpha, x, beta, beta_dev, y, w, st_check);
+  else waxpby_kernel<2><<<grid, kThreads, 0, s>>>(n, alpha, x, beta, beta_dev, y, w, st_check);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+int hpccg_dev_waxpby(int n, double alpha, const double *x, double beta, const double *y, double *w, void *stream) {
+  if (n < 0 || !x || !y || !w) return fail(HPCCG_ERR_ARG, "hpccg_dev_waxpby: bad argument");
+  return launch_waxpby(n, alpha, x, beta, nullptr, y, w, nullptr, (cudaStream_t)stream);
+}
+
+int hpccg_dev_update_xr_dot(int n, const double *alpha_dev, const double *p, const double *Ap, double *x, double *r,
+                            double *rr_dev, void *stream) {
+  if (n < 0 || !alpha_dev || !p || !Ap || !x || !r || !rr_dev) return fail(HPCCG_ERR_ARG, "hpccg_dev_update_xr_dot: bad argument");
+  if (!aligned16(p) || !aligned16(Ap) || !aligned16(x) || !aligned16(r))
+    return fail(HPCCG_ERR_ARG, "hpccg_dev_update_xr_dot: vectors must be 16-byte aligned");
+  GlobalWorkspace *w = nullptr;
+  HPCCG_TRY(global_workspace(&w));
+  std::lock_guard<std::mutex> lk(w->mu);
+  const int grid = stream_grid((n + 1) / 2);
+  update_xr_dot_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, alpha_dev, p, Ap, x, r, w->partials, grid,
+                                                                    w->counter, fin_store(rr_dev));
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+int hpccg_dev_p_update(int n, const double *beta_dev, const double *r, double *p, void *stream) {
+  if (n < 0 || !beta_dev || !r || !p) return fail(HPCCG_ERR_ARG, "hpccg_dev_p_update: bad argument");
+  return launch_waxpby(n, 1.0, r, 0.0, beta_dev, p, p, nullptr, (cudaStream_t)stream);
+}
+
+int hpccg_dev_halo_pack(const hpccg_dev_matrix *m, const double *x, double *send_buffer_dev, void *stream) {
+  if (!m || !x) return fail(HPCCG_ERR_ARG, "hpccg_dev_halo_pack: null argument");
+  if (m->total_to_be_sent == 0) return 0;
+  double *dst = send_buffer_dev ? send_buffer_dev : m->d_send_buffer;
+  halo_pack_kernel<<<stream_grid(m->total_to_be_sent), kThreads, 0, (cudaStream_t)stream>>>(
+      m->total_to_be_sent, m->d_elements_to_send, x, dst, nullptr);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+int hpccg_dev_max_abs_diff(int n, const double *v1, const double *v2, double *result_dev, void *stream) {
+  if (n < 0 || !v1 || !v2 || !result_dev) return fail(HPCCG_ERR_ARG, "hpccg_dev_max_abs_diff: bad argument");
+  GlobalWorkspace *w = nullptr;
+  HPCCG_TRY(global_workspace(&w));
+  std::lock_guard<std::mutex> lk(w->mu);
+  const int grid = stream_grid(n);
+  max_abs_diff_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n, v1, v2, w->partials, grid, w->counter, result_dev);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// The CG loop (HPCCG.cpp:312-402)
+// ================================================================================================
+namespace hpccg {
+
+enum TimerCat { T_DDOT = 1, T_WAXPBY = 2, T_SPMV = 3, T_ALLRED = 4, T_EXCH = 5, T_FUSED_SPMV = 8, T_FUSED_UPD = 9 };
+
+// Pairs of CUDA events around launches, accumulated per category after the solve.
+struct EventTimers {
+  bool on = false;
+  cudaStream_t s = nullptr;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cats;
+  size_t used = 0;
+  int open_cat = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void tick(int cat) {
+    if (!on) return;
+    open_cat = cat;
+    cudaEventRecord(get(), s);
+  }
+  void tock() {
+    if (!on) return;
+    cudaEventRecord(get(), s);
+    cats.push_back(open_cat);
+  }
+  // acc[cat] += seconds
+  void collect(double *acc, int ncat) {
+    for (size_t i = 0; i < cats.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pool[2 * i], pool[2 * i + 1]);
+      if (cats[i] < ncat) acc[cats[i]] += ms * 1e-3;
+    }
+  }
+  void reset() {
+    used = 0;
+    cats.clear();
+  }
+  ~EventTimers() {
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+};
+
+struct SolveRank {
+  hpccg_dev_matrix *m;
+  const double *b;
+  double *x;
+  int grank;  // global rank id
+};
+
+static FinishParams make_fp(int mode, hpccg_dev_matrix *m, int k, int last, double tol, bool check) {
+  FinishParams fp{};
+  fp.mode = mode;
+  fp.k = k;
+  fp.last = last;
+  fp.check_active = check ? 1 : 0;
+  fp.tol = tol;
+  fp.st = m->state;
+  fp.hist = m->hist;
+  fp.out = nullptr;
+  return fp;
+}
+
+// Halo exchange of vector v (ncol doubles) for all local ranks.  nccl: one local rank, transfers on the
+// matrix's comm stream (caller fences with events); otherwise every rank of the world is local and the
+// transfers are device copies on `s`.
+static int exchange_halo(std::vector<SolveRank> &rk, int R, bool nccl, double *const *v, const CgState *const *chk,
+                         cudaStream_t s) {
+  if (R == 1) return 0;
+  for (size_t q = 0; q < rk.size(); ++q) {
+    hpccg_dev_matrix *m = rk[q].m;
+    if (m->total_to_be_sent > 0) {
+      halo_pack_kernel<<<stream_grid(m->total_to_be_sent), kThreads, 0, s>>>(m->total_to_be_sent, m->d_elements_to_send,
+                                                                              v[q], m->d_send_buffer, chk ? chk[q] : nullptr);
+      count_launch();
+      HPCCG_LAUNCH_CHECK();
+    }
+  }
+  if (nccl) {
+    hpccg_dev_matrix *m = rk[0].m;
+    return nccl_halo_exchange(m->d_send_buffer, m->send_length.data(), v[0] + m->n, m->recv_length.data(),
+                              m->neighbors.data(), m->num_neighbors, s);
+  }
+  // in-process world: rank q receives from neighbour i the slice that neighbour packed for q
+  for (size_t q = 0; q < rk.size(); ++q) {
+    hpccg_dev_matrix *m = rk[q].m;
+    double *dst = v[q] + m->n;
+    for (int i = 0; i < m->num_neighbors; ++i) {
+      const int nb = m->neighbors[i];
+      if (nb < 0 || nb >= (int)rk.size()) return fail(HPCCG_ERR_STATE, "neighbour %d is not a local rank", nb);
+      hpccg_dev_matrix *mb = rk[nb].m;
+      const double *src = mb->d_send_buffer;
+      int found = -1;
+      for (int k = 0; k < mb->num_neighbors; ++k) {
+        if (mb->neighbors[k] == rk[q].grank) {
+          found = k;
+          break;
+        }
+        src += mb->send_length[k];
+      }
+      if (found < 0 || mb->send_length[found] != m->recv_length[i])
+        return fail(HPCCG_ERR_STATE, "halo plans of ranks %d and %d do not match", rk[q].grank, nb);
+      if (m->recv_length[i] > 0)
+        HPCCG_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * m->recv_length[i], cudaMemcpyDeviceToDevice, s));
+      dst += m->recv_length[i];
+    }
+  }
+  return 0;
+}
+
+static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_iter, double tol, int *niters_out,
+                         double *normr_out, double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t s) {
+  const int L = (int)rk.size();
+  const bool multi = R > 1;
+  const bool unfused = (flags & HPCCG_SOLVE_UNFUSED) != 0;
+  const bool overlap = nccl && !(flags & HPCCG_SOLVE_NO_OVERLAP) && !unfused;
+  if (max_iter < 1) max_iter = 1;
+  for (auto &q : rk) {
+    if (!q.m || !q.b || !q.x) return fail(HPCCG_ERR_ARG, "cg_solve: null argument");
+    if (!aligned16(q.b) || !aligned16(q.x)) return fail(HPCCG_ERR_ARG, "cg_solve: b and x must be 16-byte aligned");
+    if (multi && q.m->ncol > q.m->n && q.m->num_neighbors == 0)
+      return fail(HPCCG_ERR_STATE, "cg_solve: matrix has halo columns but no halo plan (call make_local_matrix)");
+    HPCCG_TRY(ensure_solver_workspace(q.m, max_iter, R));
+  }
+  // all local ranks share rank 0's gather array in the in-process world
+  double *gathered = rk[0].m->gathered;
+  static thread_local EventTimers timers;
+  timers.reset();
+  timers.on = (flags & HPCCG_SOLVE_TIMERS) != 0 && times != nullptr;
+  timers.s = s;
+  cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
+  HPCCG_CUDA(cudaEventCreate(&ev_loop0));
+  HPCCG_CUDA(cudaEventCreate(&ev_loop1));
+  double t4_host = 0.0;
+
+  std::vector<double *> pv(L);
+  std::vector<const CgState *> chk(L);
+  for (int q = 0; q < L; ++q) {
+    pv[q] = rk[q].m->p;
+    chk[q] = rk[q].m->state;
+  }
+
+  // -- reduction tail: local sums -> (gather) -> scalar finish on every local rank
+  auto finish_multi = [&](int mode, int k, int last, bool check) -> int {
+    timers.tick(T_ALLRED);
+    if (nccl) HPCCG_TRY(nccl_allgather_double(gathered, s));
+    for (int q = 0; q < L; ++q) {
+      cg_scalar_kernel<<<1, 32, 0, s>>>(gathered, R, make_fp(mode, rk[q].m, k, last, tol, check));
+      count_launch();
+    }
+    HPCCG_LAUNCH_CHECK();
+    timers.tock();
+    return 0;
+  };
+  auto fp_for = [&](int mode, int q, int k, int last, bool check) {
+    if (!multi) return make_fp(mode, rk[q].m, k, last, tol, check);
+    FinishParams fp = make_fp(FIN_STORE, rk[q].m, k, last, tol, check);
+    fp.out = gathered + rk[q].grank;
+    return fp;
+  };
+  auto do_exchange = [&](bool check) -> int {
+    if (!multi) return 0;
+    timers.tick(T_EXCH);
+    HPCCG_TRY(exchange_halo(rk, R, nccl, pv.data(), check ? chk.data() : nullptr, s));
+    timers.tock();
+    return 0;
+  };
+  auto spmv_dot_all = [&](int mode, int k, bool check, bool dot) -> int {
+    for (int q = 0; q < L; ++q) {
+      hpccg_dev_matrix *m = rk[q].m;
+      FinishParams fp = dot ? fp_for(mode, q, k, 0, check) : make_fp(FIN_STORE, m, k, 0, tol, check);
+      HPCCG_TRY(spmv_full(m, m->p, m->Ap, dot, fp, s));
+    }
+    return 0;
+  };
+
+  for (int q = 0; q < L; ++q) {
+    hpccg_dev_matrix *m = rk[q].m;
+    cg_state_init_kernel<<<1, 32, 0, s>>>(m->state);
+    count_launch();
+    HPCCG_CUDA(cudaMemsetAsync(m->hist, 0xFF, sizeof(double) * (max_iter + 1), s));  // NaN = "no iteration ran"
+  }
+  HPCCG_LAUNCH_CHECK();
+
+  // ---- set-up: p = x ; Ap = A p ; r = b - Ap ; rtrans = r.r (HPCCG.cpp:347-354) ----
+  timers.tick(T_WAXPBY);
+  for (int q = 0; q < L; ++q) HPCCG_TRY(launch_waxpby(rk[q].m->n, 1.0, rk[q].x, 0.0, nullptr, rk[q].x, rk[q].m->p, nullptr, s));
+  timers.tock();
+  HPCCG_TRY(do_exchange(false));
+  timers.tick(T_SPMV);
+  HPCCG_TRY(spmv_dot_all(FIN_STORE, 0, false, false));
+  timers.tock();
+  if (!unfused) {
+    timers.tick(T_WAXPBY);
+    for (int q = 0; q < L; ++q) {
+      hpccg_dev_matrix *m = rk[q].m;
+      const int grid = stream_grid(m->n);
+      residual_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, rk[q].b, m->Ap, m->r, m->partials, grid, &m->state->counter,
+                                                    fp_for(FIN_INIT, q, 0, max_iter <= 1, false));
+      count_launch();
+    }
+    HPCCG_LAUNCH_CHECK();
+    timers.tock();
+  } else {
+    timers.tick(T_WAXPBY);
+    for (int q = 0; q < L; ++q) HPCCG_TRY(launch_waxpby(rk[q].m->n, 1.0, rk[q].b, -1.0, nullptr, rk[q].m->Ap, rk[q].m->r, nullptr, s));
+    timers.tock();
+    timers.tick(T_DDOT);
+    for (int q = 0; q < L; ++q) {
+      hpccg_dev_matrix *m = rk[q].m;
+      const int grid = stream_grid((m->n + 1) / 2);
+      dot_kernel<true><<<grid, kThreads, 0, s>>>(m->n, m->r, m->r, m->partials, grid, &m->state->counter,
+                                                 fp_for(FIN_INIT, q, 0, max_iter <= 1, false));
+      count_launch();
+    }
+    HPCCG_LAUNCH_CHECK();
+    timers.tock();
+  }
+  if (multi) HPCCG_TRY(finish_multi(FIN_INIT, 0, max_iter <= 1, false));
+
+  // ---- iterations (HPCCG.cpp:358-386) ----
+  HPCCG_CUDA(cudaEventRecord(ev_loop0, s));
+  int *h_active = nullptr;
+  if (tol > 0.0) HPCCG_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+  for (int k = 1; k < max_iter; ++k) {
+    const int last = (k + 1 == max_iter) ? 1 : 0;
+    if (unfused && k > 1) {
+      // rtrans = r.r ; beta (HPCCG.cpp:366-368)
+      timers.tick(T_DDOT);
+      for (int q = 0; q < L; ++q) {
+        hpccg_dev_matrix *m = rk[q].m;
+        const int grid = stream_grid((m->n + 1) / 2);
+        // the unfused sequence evaluates the loop condition at the top of iteration k: FIN_RR of k-1
+        dot_kernel<true><<<grid, kThreads, 0, s>>>(m->n, m->r, m->r, m->partials, grid, &m->state->counter,
+                                                   fp_for(FIN_RR, q, k - 1, 0, true));
+        count_launch();
+      }
+      HPCCG_LAUNCH_CHECK();
+      timers.tock();
+      if (multi) HPCCG_TRY(finish_multi(FIN_RR, k - 1, 0, true));
+    }
+    // p = r (k==1, HPCCG.cpp:362) or p = r + beta p (:369)
+    timers.tick(T_WAXPBY);
+    for (int q = 0; q < L; ++q) {
+      hpccg_dev_matrix *m = rk[q].m;
+      if (k == 1) HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
+      else HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, &m->state->beta, m->p, m->p, m->state, s));
+    }
+    timers.tock();
+
+    if (overlap) {
+      // halo on the comm stream, interior rows meanwhile, halo-touching rows afterwards
+      hpccg_dev_matrix *m = rk[0].m;
+      HPCCG_CUDA(cudaEventRecord(m->ev_p_ready, s));
+      HPCCG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_p_ready, 0));
+      HPCCG_TRY(exchange_halo(rk, R, true, pv.data(), chk.data(), m->comm_stream));
+      HPCCG_CUDA(cudaEventRecord(m->ev_halo_done, m->comm_stream));
+      const int maxg = spmv_max_grid<true>(m->slots);
+      SpmvPlan pi = plan_range<2>(m->interior_begin, m->interior_end, maxg);
+      SpmvPlan pa = plan_range<2>(0, m->interior_begin, maxg);
+      SpmvPlan pb = plan_range<2>(m->interior_end, m->n, maxg);
+      const int total = pi.grid + pa.grid + pb.grid;
+      FinishParams fp = fp_for(FIN_PAP, 0, k, 0, true);
+      timers.tick(T_FUSED_SPMV);
+      HPCCG_TRY(launch_spmv<true>(m, m->p, m->Ap, pi, 0, total, fp, s));
+      HPCCG_CUDA(cudaStreamWaitEvent(s, m->ev_halo_done, 0));
+      HPCCG_TRY(launch_spmv<true>(m, m->p, m->Ap, pa, pi.grid, total, fp, s));
+      HPCCG_TRY(launch_spmv<true>(m, m->p, m->Ap, pb, pi.grid + pa.grid, total, fp, s));
+      timers.tock();
+    } else {
+      HPCCG_TRY(do_exchange(true));
+      if (!unfused) {
+        timers.tick(T_FUSED_SPMV);
+        HPCCG_TRY(spmv_dot_all(FIN_PAP, k, true, true));
+        timers.tock();
+      } else {
+        timers.tick(T_SPMV);
+        HPCCG_TRY(spmv_dot_all(FIN_STORE, k, true, false));
+        timers.tock();
+        timers.tick(T_DDOT);
+        for (int q = 0; q < L; ++q) {
+          hpccg_dev_matrix *m = rk[q].m;
+          const int grid = stream_grid((m->n + 1) / 2);
+          dot_kernel<false><<<grid, kThreads, 0, s>>>(m->n, m->p, m->Ap, m->partials, grid, &m->state->counter,
+                                                      fp_for(FIN_PAP, q, k, 0, true));
+          count_launch();
+        }
+        HPCCG_LAUNCH_CHECK();
+        timers.tock();
+      }
+    }
+    if (multi) HPCCG_TRY(finish_multi(FIN_PAP, k, 0, true));
+
+    // x += alpha p ; r -= alpha Ap (HPCCG.cpp:383-384) [+ r.r of the next iteration when fused]
+    if (!unfused) {
+      timers.tick(T_FUSED_UPD);
+      for (int q = 0; q < L; ++q) {
+        hpccg_dev_matrix *m = rk[q].m;
+        const int grid = stream_grid((m->n + 1) / 2);
+        update_xr_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->p, m->Ap, rk[q].x, m->r, m->partials, grid,
+                                                        &m->state->counter, fp_for(FIN_RR, q, k, last, true));
+        count_launch();
+      }
+      HPCCG_LAUNCH_CHECK();
+      timers.tock();
+      if (multi) HPCCG_TRY(finish_multi(FIN_RR, k, last, true));
+    } else {
+      timers.tick(T_WAXPBY);
+      for (int q = 0; q < L; ++q) {
+        hpccg_dev_matrix *m = rk[q].m;
+        HPCCG_TRY(launch_waxpby(m->n, 1.0, rk[q].x, 0.0, &m->state->alpha, m->p, rk[q].x, m->state, s));
+        HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, &m->state->neg_alpha, m->Ap, m->r, m->state, s));
+      }
+      timers.tock();
+    }
+    if (h_active && (k % 16 == 0)) {
+      // a positive tolerance can end the loop early; look every 16 iterations instead of every one
+      HPCCG_CUDA(cudaMemcpyAsync(h_active, &rk[0].m->state->active, sizeof(int), cudaMemcpyDeviceToHost, s));
+      HPCCG_CUDA(cudaStreamSynchronize(s));
+      if (*h_active == 0) break;
+    }
+  }
+  HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
+  if (h_active) cudaFreeHost(h_active);
+
+  // ---- results ----
+  CgState hs;
+  HPCCG_CUDA(cudaMemcpyAsync(&hs, rk[0].m->state, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+  if (hist_host) HPCCG_CUDA(cudaMemcpyAsync(hist_host, rk[0].m->hist, sizeof(double) * max_iter, cudaMemcpyDeviceToHost, s));
+  HPCCG_CUDA(cudaStreamSynchronize(s));
+  if (niters_out) *niters_out = hs.niters;
+  if (normr_out) *normr_out = hs.normr;
+  float ms = 0.f;
+  HPCCG_CUDA(cudaEventElapsedTime(&ms, ev_loop0, ev_loop1));
+  if (loop_ms) *loop_ms = ms;
+  cudaEventDestroy(ev_loop0);
+  cudaEventDestroy(ev_loop1);
+  if (times) {
+    double acc[16] = {0};
+    timers.collect(acc, 16);
+    // Fused kernels are split by the unfused algorithmic byte counts ("times[]"):
+    //   SpMV+p.Ap : 340n SpMV / 16n ddot ; update+r.r : 48n waxpby / 8n ddot
+    times[1] = acc[T_DDOT] + acc[T_FUSED_SPMV] * (16.0 / 356.0) + acc[T_FUSED_UPD] * (8.0 / 56.0);
+    times[2] = acc[T_WAXPBY] + acc[T_FUSED_UPD] * (48.0 / 56.0);
+    times[3] = acc[T_SPMV] + acc[T_FUSED_SPMV] * (340.0 / 356.0);
+    times[4] = acc[T_ALLRED] + t4_host;
+    times[5] = acc[T_EXCH];
+  }
+  return 0;
+}
+
+}  // namespace hpccg
+
+extern "C" {
+
+int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters,
+                       double *normr, double *hist_host, double *times, double *loop_ms, int flags, void *stream) {
+  if (!m) return fail(HPCCG_ERR_ARG, "hpccg_dev_cg_solve: null matrix");
+  const RankContext &c = ctx();
+  std::vector<SolveRank> rk{{m, b, x, c.rank}};
+  if (c.size > 1) {
+    if (!nccl_ready() || nccl_size() != c.size || nccl_rank() != c.rank)
+      return fail(HPCCG_ERR_STATE, "hpccg_dev_cg_solve: rank context is %d/%d but no matching NCCL communicator (hpccg_nccl_init)",
+                  c.rank, c.size);
+    return cg_solve_impl(rk, c.size, true, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags,
+                         (cudaStream_t)stream);
+  }
+  return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+}
+
+int hpccg_dev_cg_solve_group(int nranks, hpccg_dev_matrix *const *m, const double *const *b, double *const *x, int max_iter,
+                             double tolerance, int *niters, double *normr, double *hist_host, double *loop_ms, int flags,
+                             void *stream) {
+  if (nranks < 1 || !m || !b || !x) return fail(HPCCG_ERR_ARG, "hpccg_dev_cg_solve_group: bad argument");
+  std::vector<SolveRank> rk;
+  for (int q = 0; q < nranks; ++q) rk.push_back({m[q], b[q], x[q], q});
+  return cg_solve_impl(rk, nranks, false, max_iter, tolerance, niters, normr, hist_host, nullptr, loop_ms, flags,
+                       (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// device_matrix.hpp -- the opaque device mirror behind hpccg_dev_matrix (include/hpccg_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "cg_state.hpp"
+
+// HBM layout of one rank's matrix and solver workspace:
+//   vals  : double [slots][npad]   column-major ELLPACK, slot j = j-th stored entry of the row
+//   cols  : int32  [slots][npad]   local column id, -1 = padding (masked, never multiplied)
+//   npad  : local_nrow rounded up to 512 rows (one tile of the 2-rows-per-thread SpMV)
+//   r, Ap : double [npad] ; p : double [ncol_pad]  (solver temporaries, HPCCG.cpp:327-329)
+//   partials : double [kMaxPartials] block partials of the deterministic reductions
+//   state : CgState (device scalars) ; hist : double [hist_cap] residual history
+//   halo  : elements_to_send int32 [total_to_be_sent], send_buffer double [total_to_be_sent]
+struct hpccg_dev_matrix {
+  int device = 0;
+  int n = 0;        // local_nrow
+  int ncol = 0;     // local_ncol = n + externals
+  int slots = 0;
+  long long npad = 0;
+  double *vals = nullptr;
+  int *cols = nullptr;
+
+  // rows [0,interior_begin) and [interior_end,n) may reference halo columns (>= n); rows in between do not
+  int interior_begin = 0, interior_end = 0;
+
+  // halo plan (make_local_matrix.cpp:445-599)
+  int num_neighbors = 0;
+  std::vector<int> neighbors, recv_length, send_length;
+  int total_to_be_sent = 0;
+  int *d_elements_to_send = nullptr;
+  double *d_send_buffer = nullptr;
+
+  // workspace
+  double *partials = nullptr;
+  hpccg::CgState *state = nullptr;
+  double *gathered = nullptr;   // nranks doubles (multi-rank scalar gather)
+  int gathered_cap = 0;
+  double *r = nullptr, *p = nullptr, *Ap = nullptr;
+  double *hist = nullptr;
+  int hist_cap = 0;
+  double *scratch_x = nullptr, *scratch_y = nullptr;  // staging for host-pointer calls of the C++ API
+  long long scratch_cap = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_p_ready = nullptr, ev_halo_done = nullptr;
+};
+
+namespace hpccg {
+
+struct Device {
+  int sm_count = 148;
+  int id = 0;
+};
+const Device &device_info();
+
+// grid for a streaming/reduction kernel over `work_items` thread-items
+int stream_grid(long long work_items, int blocks_per_sm = 8);
+
+int ensure_solver_workspace(hpccg_dev_matrix *m, int max_iter, int nranks);
+int ensure_scratch(hpccg_dev_matrix *m, long long doubles);
+
+}  // namespace hpccg

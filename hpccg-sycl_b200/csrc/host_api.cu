@@ -1,0 +1,907 @@
+// host_api.cu -- the reference-named C++ API (include/hpccg_api.hpp) above the C-ABI device layer.
+//
+// Set-up (generate_matrix, make_local_matrix) is host code that reproduces the reference's arrays bit
+// for bit; everything on the CG path is forwarded to CUDA kernels through hpccg_dev_*.  If no CUDA
+// device is usable the device-touching functions FAIL (non-zero return / abort for the void ones, as the
+// reference aborts on its own capacity errors); there is no CPU fallback.
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hpccg_b200.h"
+#include "common.hpp"
+#include "context.hpp"
+#include "device_matrix.hpp"
+#include "include/YAML_Doc.hpp"
+#include "include/hpccg_api.hpp"
+
+using namespace hpccg;
+
+namespace {
+
+[[noreturn]] void die(const char *where) {
+  std::cerr << "hpccg_b200: " << where << ": " << hpccg_last_error() << std::endl;
+  std::abort();
+}
+
+// ---- stencil row enumeration (generate_matrix.cpp:259-281) ---------------------------------------------------
+// Calls emit(global_col, is_diag) for every stored entry of global row `currow` in the reference's order.
+template <typename F>
+inline int stencil_row(int nx, int ny, int ix, int iy, long long currow, long long total_nrow, bool seven, F &&emit) {
+  int nnzrow = 0;
+  const long long plane = (long long)nx * ny;
+  for (int sz = -1; sz <= 1; ++sz)
+    for (int sy = -1; sy <= 1; ++sy)
+      for (int sx = -1; sx <= 1; ++sx) {
+        const long long curcol = currow + sz * plane + sy * nx + sx;
+        // x and y are bounded by the block; z only by the global row range (reference :262-266)
+        if (ix + sx < 0 || ix + sx >= nx || iy + sy < 0 || iy + sy >= ny || curcol < 0 || curcol >= total_nrow) continue;
+        if (seven && sz * sz + sy * sy + sx * sx > 1) continue;
+        emit(curcol, curcol == currow);
+        ++nnzrow;
+      }
+  return nnzrow;
+}
+
+unsigned worker_count() { return std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)); }
+
+template <typename F>
+void parallel_planes(int nz, F &&fn) {
+  const unsigned nt = std::min<unsigned>(worker_count(), (unsigned)nz);
+  if (nt <= 1) {
+    fn(0, nz);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { fn((int)((long long)nz * t / nt), (int)((long long)nz * (t + 1) / nt)); });
+  for (auto &t : th) t.join();
+}
+
+// Registry of vectors handed out by generate_matrix (pinned with cudaHostRegister when a GPU exists so that
+// HPCCG()'s host<->device copies run at PCIe speed).
+std::mutex g_vec_mu;
+std::unordered_map<const void *, bool> g_vec_registered;
+
+double *new_vector(long long n, bool try_pin) {
+  double *v = new double[n];
+  bool pinned = false;
+  if (try_pin) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0)
+      pinned = cudaHostRegister(v, sizeof(double) * (size_t)n, cudaHostRegisterDefault) == cudaSuccess;
+    if (!pinned) cudaGetLastError();
+  }
+  std::lock_guard<std::mutex> lk(g_vec_mu);
+  g_vec_registered[v] = pinned;
+  return v;
+}
+
+void release_vector(double *v) {
+  if (!v) return;
+  bool pinned = false;
+  {
+    std::lock_guard<std::mutex> lk(g_vec_mu);
+    auto it = g_vec_registered.find(v);
+    if (it != g_vec_registered.end()) {
+      pinned = it->second;
+      g_vec_registered.erase(it);
+    }
+  }
+  if (pinned) cudaHostUnregister(v);
+  delete[] v;
+}
+
+bool is_device_pointer(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Thread-local staging buffers for the matrix-free calls (ddot, waxpby, compute_residual) on host pointers.
+struct Staging {
+  double *buf[3] = {nullptr, nullptr, nullptr};
+  long long cap[3] = {0, 0, 0};
+  double *result = nullptr;
+  int ensure(int i, long long n) {
+    if (cap[i] >= n) return 0;
+    if (buf[i]) cudaFree(buf[i]);
+    buf[i] = nullptr;
+    cap[i] = 0;
+    HPCCG_CUDA(cudaMalloc(&buf[i], sizeof(double) * (size_t)std::max<long long>(n, 2)));
+    cap[i] = n;
+    return 0;
+  }
+  int ensure_result() {
+    if (!result) HPCCG_CUDA(cudaMalloc(&result, sizeof(double) * 2));
+    return 0;
+  }
+};
+Staging &staging() {
+  static thread_local Staging s;
+  return s;
+}
+
+thread_local std::vector<double> t_last_history;
+
+// ---- make_local_matrix core --------------------------------------------------------------------------------
+struct HaloPlan {
+  std::vector<int> external_index;        // global ids, first-encounter order
+  std::vector<int> external_local_index;  // local column id of each, same order
+  std::vector<int> new_external;          // global ids in local-number order
+  std::vector<int> new_external_processor;
+  std::vector<int> neighbors, recv_length, send_length, elements_to_send;
+};
+
+// Receive side (make_local_matrix.cpp:105-255,358-367,489-505): scans `nrows` rows given by (nnz, inds)
+// in order, rewrites their columns in place to local ids and fills the first four vectors + neighbors /
+// recv_length of the plan.
+int localize_rows(long long nrows, const int *nnz, int *const *inds, int start_row, int stop_row, int local_nrow,
+                  const std::vector<int> &starts, HaloPlan &plan) {
+  std::unordered_map<int, int> seen;  // global id -> position in external_index
+  for (long long i = 0; i < nrows; ++i) {
+    int *row = inds[i];
+    for (int j = 0; j < nnz[i]; ++j) {
+      const int g = row[j];
+      if (start_row <= g && g <= stop_row) {
+        row[j] = g - start_row;
+      } else {
+        auto it = seen.find(g);
+        if (it == seen.end()) {
+          seen.emplace(g, (int)plan.external_index.size());
+          plan.external_index.push_back(g);
+        }
+        row[j] = -(g + 1);  // tagged external; resolved below once the numbering is known
+      }
+    }
+  }
+  const int ne = (int)plan.external_index.size();
+  const int size = (int)starts.size();
+  std::vector<int> owner(ne);
+  for (int i = 0; i < ne; ++i) {
+    int o = 0;
+    for (int j = size - 1; j >= 0; --j)
+      if (starts[j] <= plan.external_index[i]) {
+        o = j;
+        break;
+      }
+    owner[i] = o;
+  }
+  // externals of one owner get consecutive local ids; owners in first-encounter order (reference :218-230)
+  plan.external_local_index.assign(ne, -1);
+  {
+    std::vector<int> order;  // owners in first-encounter order
+    std::vector<std::vector<int>> members(size);
+    for (int i = 0; i < ne; ++i) {
+      if (members[owner[i]].empty()) order.push_back(owner[i]);
+      members[owner[i]].push_back(i);
+    }
+    int count = local_nrow;
+    for (int o : order)
+      for (int i : members[o]) plan.external_local_index[i] = count++;
+  }
+  for (long long i = 0; i < nrows; ++i) {
+    int *row = inds[i];
+    for (int j = 0; j < nnz[i]; ++j)
+      if (row[j] < 0) row[j] = plan.external_local_index[seen[-row[j] - 1]];
+  }
+  plan.new_external.assign(ne, 0);
+  plan.new_external_processor.assign(ne, 0);
+  for (int i = 0; i < ne; ++i) {
+    plan.new_external[plan.external_local_index[i] - local_nrow] = plan.external_index[i];
+    plan.new_external_processor[plan.external_local_index[i] - local_nrow] = owner[i];
+  }
+  for (int i = 0; i < ne; ++i) {
+    if (i == 0 || plan.new_external_processor[i - 1] != plan.new_external_processor[i]) {
+      plan.neighbors.push_back(plan.new_external_processor[i]);
+      plan.recv_length.push_back(0);
+    }
+    plan.recv_length.back()++;
+  }
+  return 0;
+}
+
+// Send side (make_local_matrix.cpp:283-316,376-440,507-587): every rank publishes the global ids it wants,
+// in the order it wants them; the owner reads its send lists out of that table.
+int negotiate_send_lists(int rank, int size, int start_row, HaloPlan &plan) {
+  const int ne = (int)plan.new_external.size();
+  std::vector<int> counts(size, 0);
+  HPCCG_TRY(ctx_allgather(&ne, sizeof(int), counts.data()));
+  int maxe = 0;
+  for (int c : counts) maxe = std::max(maxe, c);
+  std::vector<int> mine(2 * (size_t)std::max(maxe, 1), -1), all(2 * (size_t)std::max(maxe, 1) * size, -1);
+  for (int i = 0; i < ne; ++i) {
+    mine[i] = plan.new_external[i];
+    mine[std::max(maxe, 1) + i] = plan.new_external_processor[i];
+  }
+  HPCCG_TRY(ctx_allgather(mine.data(), sizeof(int) * (long long)mine.size(), all.data()));
+  const size_t stride = mine.size(), half = (size_t)std::max(maxe, 1);
+  // ranks that ask me for rows but that I receive nothing from are appended (reference :418-433; the
+  // reference appends in message-arrival order, here rank order -- the set is empty for these stencils)
+  for (int q = 0; q < size; ++q) {
+    if (q == rank) continue;
+    bool wants = false;
+    for (int k = 0; k < counts[q] && !wants; ++k) wants = all[q * stride + half + k] == rank;
+    if (!wants) continue;
+    bool found = false;
+    for (int nb : plan.neighbors) found = found || nb == q;
+    if (!found) {
+      plan.neighbors.push_back(q);
+      plan.recv_length.push_back(0);
+    }
+  }
+  plan.send_length.assign(plan.neighbors.size(), 0);
+  plan.elements_to_send.clear();
+  for (size_t i = 0; i < plan.neighbors.size(); ++i) {
+    const int q = plan.neighbors[i];
+    for (int k = 0; k < counts[q]; ++k)
+      if (all[q * stride + half + k] == rank) {
+        plan.elements_to_send.push_back(all[q * stride + k] - start_row);
+        plan.send_length[i]++;
+      }
+  }
+  return 0;
+}
+
+template <typename T>
+T *dup_array(const std::vector<T> &v) {
+  T *p = new T[std::max<size_t>(v.size(), 1)];
+  if (!v.empty()) std::memcpy(p, v.data(), sizeof(T) * v.size());
+  return p;
+}
+
+void install_plan(HPC_Sparse_Matrix *A, const HaloPlan &plan) {
+  A->num_external = (int)plan.external_index.size();
+  A->external_index = dup_array(plan.external_index);
+  A->external_local_index = dup_array(plan.external_local_index);
+  A->num_send_neighbors = (int)plan.neighbors.size();
+  A->neighbors = dup_array(plan.neighbors);
+  A->recv_length = dup_array(plan.recv_length);
+  A->send_length = dup_array(plan.send_length);
+  A->total_to_be_sent = (int)plan.elements_to_send.size();
+  A->elements_to_send = dup_array(plan.elements_to_send);
+  A->send_buffer = new double[std::max<size_t>(plan.elements_to_send.size(), 1)];
+  A->local_ncol = A->local_nrow + A->num_external;  // reference :595
+  A->localized = 1;
+}
+
+int get_mirror(HPC_Sparse_Matrix *A, hpccg_dev_matrix **out) {
+  if (!A) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (!A->device) {
+    if (A->size > 1 && !A->localized)
+      return fail(HPCCG_ERR_STATE, "matrix of a %d-rank job still has global column ids: call make_local_matrix first", A->size);
+    hpccg_dev_matrix *m = nullptr;
+    if (A->host_rows) {
+      HPCCG_TRY(hpccg_dev_matrix_create(A->local_nrow, A->local_ncol, A->nnz_in_row, A->ptr_to_vals_in_row,
+                                        A->ptr_to_inds_in_row, &m));
+    } else {
+      if (A->size > 1) return fail(HPCCG_ERR_STATE, "device-only matrix without mirror after make_local_matrix");
+      HPCCG_TRY(hpccg_dev_matrix_generate(A->gen_nx, A->gen_ny, A->gen_nz, 0, 1, A->gen_stencil, nullptr, nullptr,
+                                          A->local_nrow, &m));
+    }
+    if (A->localized) {
+      int rc = hpccg_dev_matrix_set_halo(m, A->num_send_neighbors, A->neighbors, A->recv_length, A->send_length,
+                                         A->elements_to_send, A->total_to_be_sent);
+      if (rc) {
+        hpccg_dev_matrix_destroy(m);
+        return rc;
+      }
+    }
+    A->device = m;
+  }
+  *out = static_cast<hpccg_dev_matrix *>(A->device);
+  return 0;
+}
+
+// Sum (or max) of one double per rank across the job, in rank order, through NCCL.
+int reduce_across_ranks(double *value, bool take_max) {
+  const RankContext &c = ctx();
+  if (c.size == 1) return 0;
+  if (!nccl_ready()) return fail(HPCCG_ERR_STATE, "rank context has %d ranks but no NCCL communicator", c.size);
+  double *d = nullptr;
+  HPCCG_CUDA(cudaMalloc(&d, sizeof(double) * c.size));
+  HPCCG_CUDA(cudaMemcpy(d + c.rank, value, sizeof(double), cudaMemcpyHostToDevice));
+  int rc = nccl_allgather_double(d, nullptr);
+  std::vector<double> all(c.size);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(all.data(), d, sizeof(double) * c.size, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail_cuda(e, "gather copy", __FILE__, __LINE__);
+  }
+  cudaFree(d);
+  if (rc) return rc;
+  double g = all[0];
+  for (int r = 1; r < c.size; ++r) g = take_max ? std::max(g, all[r]) : g + all[r];
+  *value = g;
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// generate_matrix (generate_matrix.cpp:196-307)
+// ====================================================================================================
+static int generate_matrix_impl(int nx, int ny, int nz, HPC_Sparse_Matrix **Aout, double **x, double **b, double **xexact) {
+  if (nx <= 0 || ny <= 0 || nz <= 0 || !Aout || !x || !b || !xexact) return fail(HPCCG_ERR_ARG, "generate_matrix: bad argument");
+  const RankContext &c = ctx();
+  const long long n = (long long)nx * ny * nz;
+  const long long total = n * c.size;
+  if (total > INT_MAX) return fail(HPCCG_ERR_ARG, "total_nrow %lld does not fit the reference's int row ids", total);
+  const bool seven = c.stencil == 7;
+  const bool host_rows = c.host_arrays != 0;
+  if (host_rows && 27 * n > INT_MAX)
+    return fail(HPCCG_ERR_ARG,
+                "host row arrays need 27*%lld entries, past the reference's int local_nnz (generate_matrix.cpp:223); "
+                "use hpccg_api_set_options(stencil, 0) for device-only generation", n);
+
+  HPC_Sparse_Matrix *A = new HPC_Sparse_Matrix();
+  std::memset(A, 0, sizeof *A);
+  A->start_row = (int)(n * c.rank);
+  A->stop_row = (int)(n * c.rank + n - 1);
+  A->total_nrow = (int)total;
+  A->total_nnz = 27LL * total;
+  A->local_nrow = (int)n;
+  A->local_ncol = (int)n;
+  A->local_nnz = (int)std::min<long long>(27 * n, INT_MAX);
+  A->gen_nx = nx;
+  A->gen_ny = ny;
+  A->gen_nz = nz;
+  A->gen_stencil = seven ? 7 : 27;
+  A->rank = c.rank;
+  A->size = c.size;
+  A->host_rows = host_rows ? 1 : 0;
+
+  const bool pin = true;
+  *x = new_vector(n, pin);
+  *b = new_vector(n, pin);
+  *xexact = new_vector(n, pin);
+  double *xv = *x, *bv = *b, *ev = *xexact;
+  const long long plane = (long long)nx * ny;
+  const long long start_row = A->start_row;
+
+  if (!host_rows) {
+    parallel_planes(nz, [&](int z0, int z1) {
+      for (int iz = z0; iz < z1; ++iz)
+        for (int iy = 0; iy < ny; ++iy)
+          for (int ix = 0; ix < nx; ++ix) {
+            const long long row = iz * plane + (long long)iy * nx + ix;
+            const int nnzrow = stencil_row(nx, ny, ix, iy, start_row + row, total, seven, [](long long, bool) {});
+            xv[row] = 0.0;
+            bv[row] = 27.0 - ((double)(nnzrow - 1));
+            ev[row] = 1.0;
+          }
+    });
+    *Aout = A;
+    return 0;
+  }
+
+  A->nnz_in_row = new int[n];
+  A->ptr_to_vals_in_row = new double *[n];
+  A->ptr_to_inds_in_row = new int *[n];
+  A->ptr_to_diags = new double *[n];
+  A->list_of_vals = new double[27 * n];  // sized like the reference even for the 7-pt stencil (:244-245)
+  A->list_of_inds = new int[27 * n];
+
+  // The packed lists are prefix-sum addressed, so count each z-plane first, then fill planes in parallel.
+  std::vector<long long> plane_start(nz + 1, 0);
+  parallel_planes(nz, [&](int z0, int z1) {
+    for (int iz = z0; iz < z1; ++iz) {
+      long long cnt = 0;
+      for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix)
+          cnt += stencil_row(nx, ny, ix, iy, start_row + iz * plane + (long long)iy * nx + ix, total, seven, [](long long, bool) {});
+      plane_start[iz + 1] = cnt;
+    }
+  });
+  for (int iz = 0; iz < nz; ++iz) plane_start[iz + 1] += plane_start[iz];
+
+  parallel_planes(nz, [&](int z0, int z1) {
+    for (int iz = z0; iz < z1; ++iz) {
+      double *cv = A->list_of_vals + plane_start[iz];
+      int *ci = A->list_of_inds + plane_start[iz];
+      for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+          const long long row = iz * plane + (long long)iy * nx + ix;
+          A->ptr_to_vals_in_row[row] = cv;
+          A->ptr_to_inds_in_row[row] = ci;
+          const int nnzrow = stencil_row(nx, ny, ix, iy, start_row + row, total, seven, [&](long long col, bool diag) {
+            if (diag) A->ptr_to_diags[row] = cv;
+            *cv++ = diag ? 27.0 : -1.0;
+            *ci++ = (int)col;
+          });
+          A->nnz_in_row[row] = nnzrow;
+          xv[row] = 0.0;
+          bv[row] = 27.0 - ((double)(nnzrow - 1));
+          ev[row] = 1.0;
+        }
+    }
+  });
+  *Aout = A;
+  return 0;
+}
+
+void generate_matrix(int nx, int ny, int nz, HPC_Sparse_Matrix **A, double **x, double **b, double **xexact) {
+  if (generate_matrix_impl(nx, ny, nz, A, x, b, xexact)) die("generate_matrix");
+}
+
+// ====================================================================================================
+// make_local_matrix (make_local_matrix.cpp:58-610)
+// ====================================================================================================
+static int make_local_matrix_impl(HPC_Sparse_Matrix *A) {
+  if (!A) return fail(HPCCG_ERR_ARG, "make_local_matrix: null matrix");
+  if (A->localized) return fail(HPCCG_ERR_STATE, "make_local_matrix: already localised");
+  const RankContext &c = ctx();
+  if (c.size != A->size || c.rank != A->rank)
+    return fail(HPCCG_ERR_STATE, "make_local_matrix: rank context %d/%d differs from the matrix's %d/%d", c.rank, c.size,
+                A->rank, A->size);
+  std::vector<int> starts(c.size, 0);
+  HPCCG_TRY(ctx_allgather(&A->start_row, sizeof(int), starts.data()));  // reference :172-185
+
+  HaloPlan plan;
+  if (A->host_rows) {
+    HPCCG_TRY(localize_rows(A->local_nrow, A->nnz_in_row, A->ptr_to_inds_in_row, A->start_row, A->stop_row, A->local_nrow,
+                            starts, plan));
+    HPCCG_TRY(negotiate_send_lists(c.rank, c.size, A->start_row, plan));
+    install_plan(A, plan);
+    return 0;
+  }
+
+  // Device-only matrix: only rows of the first and last z-plane can reference other ranks, and the scan
+  // visits them in the same relative order as the full scan, so the plan from those rows alone is identical.
+  const int nx = A->gen_nx, ny = A->gen_ny, nz = A->gen_nz;
+  const bool seven = A->gen_stencil == 7;
+  const long long plane = (long long)nx * ny;
+  std::vector<int> zs;
+  zs.push_back(0);
+  if (nz > 1) zs.push_back(nz - 1);
+  std::vector<int> nnz;
+  std::vector<int> flat;
+  std::vector<size_t> offs;
+  for (int iz : zs)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        offs.push_back(flat.size());
+        const long long row = iz * plane + (long long)iy * nx + ix;
+        nnz.push_back(stencil_row(nx, ny, ix, iy, (long long)A->start_row + row, A->total_nrow, seven,
+                                  [&](long long col, bool) { flat.push_back((int)col); }));
+      }
+  std::vector<int *> rows(offs.size());
+  for (size_t i = 0; i < offs.size(); ++i) rows[i] = flat.data() + offs[i];
+  HPCCG_TRY(localize_rows((long long)rows.size(), nnz.data(), rows.data(), A->start_row, A->stop_row, A->local_nrow, starts, plan));
+  HPCCG_TRY(negotiate_send_lists(c.rank, c.size, A->start_row, plan));
+  install_plan(A, plan);
+
+  // plane position -> local column id for the two neighbouring planes
+  std::vector<int> lower, upper;
+  if (c.rank > 0) lower.assign(plane, -1);
+  if (c.rank < c.size - 1) upper.assign(plane, -1);
+  for (size_t i = 0; i < plan.external_index.size(); ++i) {
+    const long long g = plan.external_index[i];
+    if (g < A->start_row) {
+      const long long q = g - ((long long)A->start_row - plane);
+      if (q < 0 || q >= plane || lower.empty()) return fail(HPCCG_ERR_STATE, "external %lld is not in the lower neighbour plane", g);
+      lower[q] = plan.external_local_index[i];
+    } else {
+      const long long q = g - ((long long)A->stop_row + 1);
+      if (q < 0 || q >= plane || upper.empty()) return fail(HPCCG_ERR_STATE, "external %lld is not in the upper neighbour plane", g);
+      upper[q] = plan.external_local_index[i];
+    }
+  }
+  hpccg_dev_matrix *m = nullptr;
+  HPCCG_TRY(hpccg_dev_matrix_generate(nx, ny, nz, c.rank, c.size, A->gen_stencil, lower.empty() ? nullptr : lower.data(),
+                                      upper.empty() ? nullptr : upper.data(), A->local_ncol, &m));
+  int rc = hpccg_dev_matrix_set_halo(m, A->num_send_neighbors, A->neighbors, A->recv_length, A->send_length,
+                                     A->elements_to_send, A->total_to_be_sent);
+  if (rc) {
+    hpccg_dev_matrix_destroy(m);
+    return rc;
+  }
+  A->device = m;
+  return 0;
+}
+
+void make_local_matrix(HPC_Sparse_Matrix *A) {
+  if (make_local_matrix_impl(A)) die("make_local_matrix");
+}
+
+void destroyMatrix(HPC_Sparse_Matrix *&A) {
+  if (!A) return;
+  delete[] A->title;
+  delete[] A->nnz_in_row;
+  delete[] A->list_of_vals;
+  delete[] A->ptr_to_vals_in_row;
+  delete[] A->list_of_inds;
+  delete[] A->ptr_to_inds_in_row;
+  delete[] A->ptr_to_diags;
+  delete[] A->external_index;
+  delete[] A->external_local_index;
+  delete[] A->elements_to_send;
+  delete[] A->neighbors;
+  delete[] A->recv_length;
+  delete[] A->send_length;
+  delete[] A->send_buffer;
+  if (A->device) hpccg_dev_matrix_destroy(static_cast<hpccg_dev_matrix *>(A->device));
+  delete A;
+  A = 0;
+}
+
+void free_vectors(double *x, double *b, double *xexact) {
+  release_vector(x);
+  release_vector(b);
+  release_vector(xexact);
+}
+
+double mytimer(void) {
+  using clk = std::chrono::steady_clock;
+  static const clk::time_point t0 = clk::now();
+  return std::chrono::duration<double>(clk::now() - t0).count();
+}
+
+// ====================================================================================================
+// Kernels behind the reference names
+// ====================================================================================================
+int HPC_sparsemv(HPC_Sparse_Matrix *A, const double *const x, double *const y) {
+  hpccg_dev_matrix *m = nullptr;
+  HPCCG_TRY(get_mirror(A, &m));
+  const bool xd = is_device_pointer(x), yd = is_device_pointer(y);
+  const double *dx = x;
+  double *dy = y;
+  if (!xd || !yd) HPCCG_TRY(ensure_scratch(m, std::max<long long>(m->npad, m->ncol + 2)));
+  if (!xd) {
+    HPCCG_CUDA(cudaMemcpy(m->scratch_x, x, sizeof(double) * m->ncol, cudaMemcpyHostToDevice));
+    dx = m->scratch_x;
+  }
+  if (!yd) dy = m->scratch_y;
+  HPCCG_TRY(hpccg_dev_spmv(m, dx, dy, nullptr));
+  if (!yd) HPCCG_CUDA(cudaMemcpy(y, dy, sizeof(double) * m->n, cudaMemcpyDeviceToHost));
+  else HPCCG_CUDA(cudaStreamSynchronize(nullptr));
+  return 0;
+}
+
+static int exchange_externals_impl(HPC_Sparse_Matrix *A, double *x) {
+  hpccg_dev_matrix *m = nullptr;
+  HPCCG_TRY(get_mirror(A, &m));
+  if (A->size == 1) return 0;
+  if (!nccl_ready()) return fail(HPCCG_ERR_STATE, "exchange_externals needs the NCCL communicator (hpccg_nccl_init)");
+  const bool xd = is_device_pointer(x);
+  double *dx = x;
+  if (!xd) {
+    HPCCG_TRY(ensure_scratch(m, std::max<long long>(m->npad, m->ncol + 2)));
+    HPCCG_CUDA(cudaMemcpy(m->scratch_x, x, sizeof(double) * m->n, cudaMemcpyHostToDevice));
+    dx = m->scratch_x;
+  }
+  HPCCG_TRY(hpccg_dev_halo_pack(m, dx, nullptr, nullptr));
+  HPCCG_TRY(nccl_halo_exchange(m->d_send_buffer, m->send_length.data(), dx + m->n, m->recv_length.data(), m->neighbors.data(),
+                               m->num_neighbors, nullptr));
+  if (!xd) HPCCG_CUDA(cudaMemcpy(x + m->n, dx + m->n, sizeof(double) * (m->ncol - m->n), cudaMemcpyDeviceToHost));
+  else HPCCG_CUDA(cudaStreamSynchronize(nullptr));
+  return 0;
+}
+
+void exchange_externals(HPC_Sparse_Matrix *A, const double *x) {
+  // the reference casts the const away as well (exchange_externals.cpp:84)
+  if (exchange_externals_impl(A, const_cast<double *>(x))) die("exchange_externals");
+}
+
+int ddot(const int n, const double *const x, const double *const y, double *const result, double &time_allreduce) {
+  if (n < 0 || !x || !y || !result) return fail(HPCCG_ERR_ARG, "ddot: bad argument");
+  Staging &st = staging();
+  HPCCG_TRY(st.ensure_result());
+  const bool same = (x == y);
+  const double *dx = x, *dy = y;
+  if (!is_device_pointer(x)) {
+    HPCCG_TRY(st.ensure(0, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[0], x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    dx = st.buf[0];
+  }
+  if (same) {
+    dy = dx;
+  } else if (!is_device_pointer(y)) {
+    HPCCG_TRY(st.ensure(1, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[1], y, sizeof(double) * n, cudaMemcpyHostToDevice));
+    dy = st.buf[1];
+  }
+  HPCCG_TRY(hpccg_dev_dot(n, dx, dy, st.result, nullptr));
+  double local = 0.0;
+  HPCCG_CUDA(cudaMemcpy(&local, st.result, sizeof(double), cudaMemcpyDeviceToHost));
+  if (ctx().size > 1) {
+    const double t0 = mytimer();  // ddot.cpp:77-82
+    HPCCG_TRY(reduce_across_ranks(&local, false));
+    time_allreduce += mytimer() - t0;
+  }
+  *result = local;
+  return 0;
+}
+
+int waxpby(const int n, const double alpha, const double *const x, const double beta, const double *const y, double *const w) {
+  if (n < 0 || !x || !y || !w) return fail(HPCCG_ERR_ARG, "waxpby: bad argument");
+  Staging &st = staging();
+  const bool wd = is_device_pointer(w);
+  // aliasing (w==x, w==y, x==y) must survive staging: map equal host pointers to equal device buffers
+  const double *dx = x, *dy = y;
+  double *dw = w;
+  if (!is_device_pointer(x)) {
+    HPCCG_TRY(st.ensure(0, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[0], x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    dx = st.buf[0];
+  }
+  if (y == x) dy = dx;
+  else if (!is_device_pointer(y)) {
+    HPCCG_TRY(st.ensure(1, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[1], y, sizeof(double) * n, cudaMemcpyHostToDevice));
+    dy = st.buf[1];
+  }
+  if (!wd) {
+    if (w == x) dw = const_cast<double *>(dx);
+    else if (w == y) dw = const_cast<double *>(dy);
+    else {
+      HPCCG_TRY(st.ensure(2, n));
+      dw = st.buf[2];
+    }
+  }
+  HPCCG_TRY(hpccg_dev_waxpby(n, alpha, dx, beta, dy, dw, nullptr));
+  if (!wd) HPCCG_CUDA(cudaMemcpy(w, dw, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  else HPCCG_CUDA(cudaStreamSynchronize(nullptr));
+  return 0;
+}
+
+int compute_residual(const int n, const double *const v1, const double *const v2, double *const residual) {
+  if (n < 0 || !v1 || !v2 || !residual) return fail(HPCCG_ERR_ARG, "compute_residual: bad argument");
+  Staging &st = staging();
+  HPCCG_TRY(st.ensure_result());
+  const double *d1 = v1, *d2 = v2;
+  if (!is_device_pointer(v1)) {
+    HPCCG_TRY(st.ensure(0, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[0], v1, sizeof(double) * n, cudaMemcpyHostToDevice));
+    d1 = st.buf[0];
+  }
+  if (!is_device_pointer(v2)) {
+    HPCCG_TRY(st.ensure(1, n));
+    HPCCG_CUDA(cudaMemcpy(st.buf[1], v2, sizeof(double) * n, cudaMemcpyHostToDevice));
+    d2 = st.buf[1];
+  }
+  HPCCG_TRY(hpccg_dev_max_abs_diff(n, d1, d2, st.result, nullptr));
+  double local = 0.0;
+  HPCCG_CUDA(cudaMemcpy(&local, st.result, sizeof(double), cudaMemcpyDeviceToHost));
+  HPCCG_TRY(reduce_across_ranks(&local, true));  // compute_residual.cpp:73 (MPI_MAX)
+  *residual = local;
+  return 0;
+}
+
+// ====================================================================================================
+// HPCCG (HPCCG.cpp:312-402)
+// ====================================================================================================
+int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_iter, const double tolerance, int &niters,
+          double &normr, double *times) {
+  const double t_begin = mytimer();
+  hpccg_dev_matrix *m = nullptr;
+  HPCCG_TRY(get_mirror(A, &m));
+  const bool bd = is_device_pointer(b), xd = is_device_pointer(x);
+  const double *db = b;
+  double *dx = x;
+  if (!bd || !xd) HPCCG_TRY(ensure_scratch(m, std::max<long long>(m->npad, m->ncol + 2)));
+  if (!xd) {
+    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_x, x, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
+    dx = m->scratch_x;
+  }
+  if (!bd) {
+    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_y, b, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
+    db = m->scratch_y;
+  }
+  const int iters = std::max(max_iter, 1);
+  t_last_history.assign(iters, std::nan(""));
+  double local_times[7] = {0, 0, 0, 0, 0, 0, 0};
+  int flags = HPCCG_SOLVE_TIMERS;
+  if (const char *e = std::getenv("HPCCG_B200_UNFUSED"))
+    if (e[0] == '1') flags |= HPCCG_SOLVE_UNFUSED;
+  int it = 0;
+  double nr = 0.0;
+  HPCCG_TRY(hpccg_dev_cg_solve(m, db, dx, max_iter, tolerance, &it, &nr, t_last_history.data(), local_times, nullptr, flags, nullptr));
+  if (!xd) HPCCG_CUDA(cudaMemcpy(x, dx, sizeof(double) * m->n, cudaMemcpyDeviceToHost));
+  niters = it;
+  normr = nr;
+
+  // Residual lines of HPCCG.cpp:356,372-373, printed after the device-resident loop has finished.
+  if (ctx().rank == 0) {
+    int print_freq = max_iter / 10;  // HPCCG.cpp:342-344
+    if (print_freq > 50) print_freq = 50;
+    if (print_freq < 1) print_freq = 1;
+    std::cout << "Initial Residual = " << t_last_history[0] << std::endl;
+    for (int k = 1; k <= it; ++k)
+      if (k % print_freq == 0 || k + 1 == max_iter) std::cout << "Iteration = " << k << "   Residual = " << t_last_history[k] << std::endl;
+  }
+  if (times) {
+    for (int i = 1; i <= 5; ++i) times[i] = local_times[i];
+    times[0] = mytimer() - t_begin;  // HPCCG.cpp:399
+  }
+  return 0;
+}
+
+// ====================================================================================================
+// C views for FFI callers
+// ====================================================================================================
+extern "C" {
+
+int hpccg_api_set_options(int stencil, int host_arrays) {
+  if (stencil != 27 && stencil != 7) return fail(HPCCG_ERR_ARG, "stencil must be 27 or 7");
+  ctx().stencil = stencil;
+  ctx().host_arrays = host_arrays ? 1 : 0;
+  return 0;
+}
+
+int hpccg_api_generate_matrix(int nx, int ny, int nz, void **A, double **x, double **b, double **xexact) {
+  return generate_matrix_impl(nx, ny, nz, reinterpret_cast<HPC_Sparse_Matrix **>(A), x, b, xexact);
+}
+
+int hpccg_api_make_local_matrix(void *A) { return make_local_matrix_impl(static_cast<HPC_Sparse_Matrix *>(A)); }
+
+int hpccg_api_HPCCG(void *A, double *b, double *x, int max_iter, double tolerance, int *niters, double *normr, double *times) {
+  int it = 0;
+  double nr = 0.0;
+  int rc = HPCCG(static_cast<HPC_Sparse_Matrix *>(A), b, x, max_iter, tolerance, it, nr, times);
+  if (niters) *niters = it;
+  if (normr) *normr = nr;
+  return rc;
+}
+
+int hpccg_api_HPC_sparsemv(void *A, const double *x, double *y) { return HPC_sparsemv(static_cast<HPC_Sparse_Matrix *>(A), x, y); }
+
+int hpccg_api_ddot(int n, const double *x, const double *y, double *result, double *time_allreduce) {
+  double t = 0.0;
+  int rc = ddot(n, x, y, result, t);
+  if (time_allreduce) *time_allreduce += t;
+  return rc;
+}
+
+int hpccg_api_waxpby(int n, double alpha, const double *x, double beta, const double *y, double *w) {
+  return waxpby(n, alpha, x, beta, y, w);
+}
+
+int hpccg_api_exchange_externals(void *A, double *x) { return exchange_externals_impl(static_cast<HPC_Sparse_Matrix *>(A), x); }
+
+int hpccg_api_compute_residual(int n, const double *v1, const double *v2, double *residual) {
+  return compute_residual(n, v1, v2, residual);
+}
+
+int hpccg_api_destroyMatrix(void *A) {
+  HPC_Sparse_Matrix *p = static_cast<HPC_Sparse_Matrix *>(A);
+  destroyMatrix(p);
+  return 0;
+}
+
+int hpccg_api_free_vectors(double *x, double *b, double *xexact) {
+  free_vectors(x, b, xexact);
+  return 0;
+}
+
+long long hpccg_api_matrix_scalar(const void *Av, const char *f) {
+  const HPC_Sparse_Matrix *A = static_cast<const HPC_Sparse_Matrix *>(Av);
+  if (!A || !f) return -1;
+  const std::string s(f);
+  if (s == "start_row") return A->start_row;
+  if (s == "stop_row") return A->stop_row;
+  if (s == "total_nrow") return A->total_nrow;
+  if (s == "total_nnz") return A->total_nnz;
+  if (s == "local_nrow") return A->local_nrow;
+  if (s == "local_ncol") return A->local_ncol;
+  if (s == "local_nnz") return A->local_nnz;
+  if (s == "num_external") return A->num_external;
+  if (s == "num_send_neighbors") return A->num_send_neighbors;
+  if (s == "total_to_be_sent") return A->total_to_be_sent;
+  if (s == "host_rows") return A->host_rows;
+  if (s == "localized") return A->localized;
+  if (s == "nnz_sum") {
+    if (!A->host_rows) return -1;
+    long long t = 0;
+    for (int i = 0; i < A->local_nrow; ++i) t += A->nnz_in_row[i];
+    return t;
+  }
+  return -1;
+}
+
+long long hpccg_api_matrix_array(const void *Av, const char *f, void *dst, long long cap) {
+  const HPC_Sparse_Matrix *A = static_cast<const HPC_Sparse_Matrix *>(Av);
+  if (!A || !f) return -1;
+  const std::string s(f);
+  const long long n = A->local_nrow;
+  auto out = [&](const void *src, size_t elt, long long count) -> long long {
+    if (dst && cap >= count && count > 0) std::memcpy(dst, src, elt * (size_t)count);
+    return count;
+  };
+  if (s == "external_index") return out(A->external_index, sizeof(int), A->num_external);
+  if (s == "external_local_index") return out(A->external_local_index, sizeof(int), A->num_external);
+  if (s == "elements_to_send") return out(A->elements_to_send, sizeof(int), A->total_to_be_sent);
+  if (s == "neighbors") return out(A->neighbors, sizeof(int), A->num_send_neighbors);
+  if (s == "recv_length") return out(A->recv_length, sizeof(int), A->num_send_neighbors);
+  if (s == "send_length") return out(A->send_length, sizeof(int), A->num_send_neighbors);
+  if (!A->host_rows) return -1;
+  if (s == "nnz_in_row") return out(A->nnz_in_row, sizeof(int), n);
+  const long long nnz_sum = hpccg_api_matrix_scalar(A, "nnz_sum");
+  if (s == "list_of_inds") return out(A->list_of_inds, sizeof(int), nnz_sum);
+  if (s == "list_of_vals") return out(A->list_of_vals, sizeof(double), nnz_sum);
+  if (s == "ind_offsets" || s == "val_offsets" || s == "diag_offsets") {
+    if (dst && cap >= n) {
+      long long *o = static_cast<long long *>(dst);
+      for (long long i = 0; i < n; ++i) {
+        if (s == "ind_offsets") o[i] = A->ptr_to_inds_in_row[i] - A->list_of_inds;
+        else if (s == "val_offsets") o[i] = A->ptr_to_vals_in_row[i] - A->list_of_vals;
+        else o[i] = A->ptr_to_diags[i] - A->list_of_vals;
+      }
+    }
+    return n;
+  }
+  return -1;
+}
+
+int hpccg_api_matrix_device(void *A, hpccg_dev_matrix **out) {
+  hpccg_dev_matrix *m = nullptr;
+  HPCCG_TRY(get_mirror(static_cast<HPC_Sparse_Matrix *>(A), &m));
+  if (out) *out = m;
+  return 0;
+}
+
+int hpccg_api_last_history(double *hist, int capacity) {
+  const int n = (int)t_last_history.size();
+  if (hist && capacity >= n && n > 0) std::memcpy(hist, t_last_history.data(), sizeof(double) * n);
+  return n;
+}
+
+// Report assembly of main.cpp:214-305 through this library's YAML_Doc.
+int hpccg_api_yaml_report(int nx, int ny, int nz, int niters, double normr, const double *times, double total_nrow,
+                          double total_nnz, int ranks, int omp_threads, const double *t4stats, char *out, int capacity) {
+  const double it = niters;
+  const double f_ddot = it * 4 * total_nrow, f_waxpby = it * 6 * total_nrow, f_spmv = it * 2 * total_nnz;
+  const double f_all = f_ddot + f_waxpby + f_spmv;
+  YAML_Doc doc("hpccg", "1.0");
+  YAML_Element *par = doc.add("Parallelism", "");
+  if (ranks > 0) par->add("Number of MPI ranks", ranks);
+  else par->add("MPI not enabled", "");
+  if (omp_threads > 0) par->add("Number of OpenMP threads", omp_threads);
+  else par->add("OpenMP not enabled", "");
+  par->add("SYCL not enabled", "");
+  YAML_Element *dim = doc.add("Dimensions", "");
+  dim->add("nx", nx);
+  dim->add("ny", ny);
+  dim->add("nz", nz);
+  doc.add("Number of iterations", niters);
+  doc.add("Final residual", normr);
+  doc.add("#********** Performance Summary (times in sec) ***********", "");
+  const char *rows[4] = {"Total   ", "DDOT    ", "WAXPBY  ", "SPARSEMV"};
+  const double flops[4] = {f_all, f_ddot, f_waxpby, f_spmv};
+  YAML_Element *ts = doc.add("Time Summary", "");
+  for (int i = 0; i < 4; ++i) ts->add(rows[i], times[i]);
+  YAML_Element *fs = doc.add("FLOPS Summary", "");
+  for (int i = 0; i < 4; ++i) fs->add(rows[i], flops[i]);
+  YAML_Element *ms = doc.add("MFLOPS Summary", "");
+  for (int i = 0; i < 4; ++i) ms->add(rows[i], flops[i] / times[i] / 1.0E6);
+  if (ranks > 0) {
+    YAML_Element *dv = doc.add("DDOT Timing Variations", "");
+    dv->add("Min DDOT MPI_Allreduce time", t4stats ? t4stats[0] : 0.0);
+    dv->add("Max DDOT MPI_Allreduce time", t4stats ? t4stats[1] : 0.0);
+    dv->add("Avg DDOT MPI_Allreduce time", t4stats ? t4stats[2] : 0.0);
+    const double with_overhead = times[3] + times[5] + times[6];
+    YAML_Element *ov = doc.add("SPARSEMV OVERHEADS", "");
+    ov->add("SPARSEMV MFLOPS W OVERHEAD", f_spmv / with_overhead / 1.0E6);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Time", times[5] + times[6]);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Pct", (times[5] + times[6]) / with_overhead * 100.0);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Setup Time", times[6]);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Setup Pct", times[6] / with_overhead * 100.0);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Time", times[5]);
+    ov->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Pct", times[5] / with_overhead * 100.0);
+  }
+  const std::string text = doc.generateYAML();
+  if ((int)text.size() + 1 > capacity) return -(int)text.size() - 1;
+  std::memcpy(out, text.c_str(), text.size() + 1);
+  return (int)text.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+// HPCCG.hpp -- forwarding header: same include name as the reference, declarations in hpccg_api.hpp.
+#pragma once
+#include "hpccg_api.hpp"

@@ -1,0 +1,3 @@
+// compute_residual.hpp -- forwarding header: same include name as the reference, declarations in hpccg_api.hpp.
+#pragma once
+#include "hpccg_api.hpp"

@@ -1,0 +1,435 @@
+// kernels.cuh -- the hand-written sm_100a kernels of the HPCCG hot path.
+//
+// All kernels are HBM-bandwidth bound (arithmetic intensity ~0.155 flop/B);
+// nothing here is a dense contraction, so no tensor cores.  Design rules applied:
+//   * column-major ELLPACK so that a warp reads 32 (or 64) consecutive rows of one slot:
+//     every matrix load is a fully coalesced 128-bit (vals) / 64-bit (cols) access;
+//   * the matrix stream is read once with ld.global.nc.L1::no_allocate so it does not evict the
+//     gathered vector from L1; the vector x is gathered through L1/L2 (__ldg);
+//   * persistent grid-stride tiles, grid = a multiple of the SM count, so reductions have a small,
+//     fixed number of block partials and a deterministic two-pass finish;
+//   * products and sums use __dmul_rn/__dadd_rn (never contracted into FMA) in the reference's
+//     stored-entry order, which makes HPC_sparsemv and waxpby bit-identical to the reference's
+//     g++ -O3 x86-64 build (it emits no FMA); only reduction order differs in ddot.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "cg_state.hpp"
+
+namespace hpccg {
+
+// What the thread that holds a finished reduction does with it.
+enum FinishMode : int {
+  FIN_STORE = 0,   // *out = sum                     (public ops, multi-rank local sums)
+  FIN_INIT = 1,    // rtrans = sum, normr, hist[0]   (HPCCG.cpp:353-356)
+  FIN_PAP = 2,     // alpha = rtrans / sum, niters=k (HPCCG.cpp:381-382,385)
+  FIN_RR = 3,      // next iteration's rtrans, beta  (HPCCG.cpp:366-368,371) + loop condition (:358)
+};
+
+struct FinishParams {
+  int mode;
+  int k;            // iteration the reduction belongs to
+  int last;         // FIN_RR: k+1 == max_iter, i.e. no further iteration will be enqueued
+  int check_active; // kernel returns at once when st->active == 0
+  double tol;
+  CgState *st;
+  double *out;      // FIN_STORE target
+  double *hist;     // residual history (device), may be null
+};
+
+__device__ __forceinline__ void cg_finish(const FinishParams &fp, double sum) {
+  CgState *st = fp.st;
+  switch (fp.mode) {
+    case FIN_STORE:
+      *fp.out = sum;
+      break;
+    case FIN_INIT:
+      st->rtrans = sum;
+      st->normr = sqrt(sum);
+      if (fp.hist) fp.hist[0] = st->normr;
+      st->niters = 0;
+      // condition of the first iteration: k=1 < max_iter (fp.last == 0) && normr > tolerance
+      st->active = (!fp.last && st->normr > fp.tol) ? 1 : 0;
+      if (st->active && fp.hist) fp.hist[1] = st->normr;  // iteration 1 prints the same normr (HPCCG.cpp:362,371)
+      break;
+    case FIN_PAP:
+      st->pAp = sum;
+      st->alpha = st->rtrans / sum;
+      st->neg_alpha = -st->alpha;
+      st->niters = fp.k;
+      break;
+    case FIN_RR: {
+      // `sum` is r.r after iteration k's update = the rtrans iteration k+1 would compute first
+      // (HPCCG.cpp:367).  Iteration k+1 runs iff k+1 < max_iter and normr_k > tolerance (:358).
+      const bool next = !fp.last && (st->normr > fp.tol);
+      if (next) {
+        st->oldrtrans = st->rtrans;
+        st->rtrans = sum;
+        st->beta = sum / st->oldrtrans;
+        st->normr = sqrt(sum);
+        if (fp.hist) fp.hist[fp.k + 1] = st->normr;
+      } else {
+        st->active = 0;
+      }
+      break;
+    }
+  }
+}
+
+// ---- streaming loads -------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int2 ld_stream_s32x2(const int *p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---- deterministic block reduction + last-block finish ---------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the block in a fixed order; result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *smem /* kThreads/32 doubles */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = (lane < (kThreads >> 5)) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// Publishes this block's partial; the block that takes the last ticket sums all partials in index
+// order (fixed tree, independent of which block happens to be last) and runs the finish action.
+__device__ __forceinline__ void publish_and_finish(double block_total, double *partials, int partial_index,
+                                                   int total_partials, unsigned *counter, const FinishParams &fp,
+                                                   double *smem) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    partials[partial_index] = block_total;
+    __threadfence();
+    const unsigned ticket = atomicInc(counter, (unsigned)(total_partials - 1));  // wraps to 0 for the next launch
+    s_last = (ticket == (unsigned)(total_partials - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < total_partials; i += kThreads) acc = __dadd_rn(acc, __ldcg(partials + i));
+  acc = block_sum(acc, smem);
+  if (threadIdx.x == 0) cg_finish(fp, acc);
+}
+
+// ---- HPC_sparsemv.cpp:68-89 on column-major ELL -----------------------------------------------------
+// SLOTS > 0: compile-time slot count (27, 7), fully unrolled so all matrix loads of a row pair are in
+// flight before the first gather.  SLOTS == 0: run-time slot count.  RPT rows per thread (2 = 128-bit
+// value loads).  Rows [row_begin,row_end) are processed; tiles start at the even row below row_begin.
+template <int SLOTS, int RPT, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_ell_kernel(const double *__restrict__ vals, const int *__restrict__ cols, long long npad, int slots_rt,
+                const double *__restrict__ x, double *__restrict__ y, int row_begin, int row_end, int tiles,
+                double *partials, int partial_offset, int total_partials, unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+  const int slots = SLOTS > 0 ? SLOTS : slots_rt;
+  constexpr int kTileRows = kThreads * RPT;
+  const int base = row_begin & ~(RPT - 1);
+  double dot = 0.0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int r0 = base + tile * kTileRows + threadIdx.x * RPT;
+    if (r0 >= row_end) continue;
+    if (RPT == 2) {
+      double s0 = 0.0, s1 = 0.0;
+      const double *vp = vals + r0;
+      const int *cp = cols + r0;
+#pragma unroll
+      for (int j = 0; j < slots; ++j) {
+        const double2 v = ld_stream_f64x2(vp + (long long)j * npad);
+        const int2 c = ld_stream_s32x2(cp + (long long)j * npad);
+        if (c.x >= 0) s0 = __dadd_rn(s0, __dmul_rn(v.x, __ldg(x + c.x)));
+        if (c.y >= 0) s1 = __dadd_rn(s1, __dmul_rn(v.y, __ldg(x + c.y)));
+      }
+      const bool in0 = r0 >= row_begin, in1 = r0 + 1 < row_end;
+      if (in0 && in1) {
+        *reinterpret_cast<double2 *>(y + r0) = make_double2(s0, s1);
+      } else {
+        if (in0) y[r0] = s0;
+        if (in1) y[r0 + 1] = s1;
+      }
+      if (DOT) {
+        if (in0) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + r0), s0));
+        if (in1) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + r0 + 1), s1));
+      }
+    } else {
+      double s0 = 0.0;
+      const double *vp = vals + r0;
+      const int *cp = cols + r0;
+#pragma unroll
+      for (int j = 0; j < slots; ++j) {
+        const double v = ld_stream_f64(vp + (long long)j * npad);
+        const int c = ld_stream_s32(cp + (long long)j * npad);
+        if (c >= 0) s0 = __dadd_rn(s0, __dmul_rn(v, __ldg(x + c)));
+      }
+      y[r0] = s0;
+      if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + r0), s0));
+    }
+  }
+  if (DOT) {
+    const double total = block_sum(dot, smem);
+    publish_and_finish(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, smem);
+  }
+}
+
+// ---- ddot.cpp:60-74 ----------------------------------------------------------------------------------
+template <bool SAME>
+__global__ void __launch_bounds__(kThreads)
+dot_kernel(int n, const double *__restrict__ x, const double *__restrict__ y, double *partials, int total_partials,
+           unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+  double acc = 0.0;
+  const int npair = n >> 1;
+  const bool aligned = ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(y)) & 15) == 0;
+  if (aligned) {
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+      const double2 a = ld_stream_f64x2(x + 2 * (long long)i);
+      const double2 b = SAME ? a : ld_stream_f64x2(y + 2 * (long long)i);
+      acc = __dadd_rn(acc, __dmul_rn(a.x, b.x));
+      acc = __dadd_rn(acc, __dmul_rn(a.y, b.y));
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) acc = __dadd_rn(acc, __dmul_rn(x[n - 1], y[n - 1]));
+  } else {
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+      acc = __dadd_rn(acc, __dmul_rn(x[i], y[i]));
+  }
+  const double total = block_sum(acc, smem);
+  publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
+}
+
+// ---- waxpby.cpp:69-93 -------------------------------------------------------------------------------
+// BRANCH 0: alpha==1 -> x + beta*y ; 1: beta==1 -> alpha*x + y ; 2: general.  Element-wise, so the
+// aliasing the reference uses (w==x, w==y, x==y) is safe; no __restrict__ on purpose.
+template <int BRANCH>
+__device__ __forceinline__ double waxpby_elem(double alpha, double x, double beta, double y) {
+  if (BRANCH == 0) return __dadd_rn(x, __dmul_rn(beta, y));
+  if (BRANCH == 1) return __dadd_rn(__dmul_rn(alpha, x), y);
+  return __dadd_rn(__dmul_rn(alpha, x), __dmul_rn(beta, y));
+}
+
+template <int BRANCH>
+__global__ void __launch_bounds__(kThreads)
+waxpby_kernel(int n, double alpha, const double *x, double beta, const double *beta_dev, const double *y, double *w,
+              const CgState *st_check) {
+  if (st_check && st_check->active == 0) return;
+  if (beta_dev) beta = *beta_dev;
+  const bool aligned =
+      ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(y) | reinterpret_cast<size_t>(w)) & 15) == 0;
+  if (aligned) {
+    const int npair = n >> 1;
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+      const double2 a = *reinterpret_cast<const double2 *>(x + 2 * (long long)i);
+      const double2 b = *reinterpret_cast<const double2 *>(y + 2 * (long long)i);
+      double2 o;
+      o.x = waxpby_elem<BRANCH>(alpha, a.x, beta, b.x);
+      o.y = waxpby_elem<BRANCH>(alpha, a.y, beta, b.y);
+      *reinterpret_cast<double2 *>(w + 2 * (long long)i) = o;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) w[n - 1] = waxpby_elem<BRANCH>(alpha, x[n - 1], beta, y[n - 1]);
+  } else {
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+      w[i] = waxpby_elem<BRANCH>(alpha, x[i], beta, y[i]);
+  }
+}
+
+// ---- HPCCG.cpp:383-384 fused with the r.r of :367 ------------------------------------------------------
+// x = x + alpha*p ; r = r + (-alpha)*Ap ; partial r.r.  alpha is read from device memory.
+__global__ void __launch_bounds__(kThreads)
+update_xr_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ p, const double *__restrict__ Ap,
+                     double *__restrict__ x, double *__restrict__ r, double *partials, int total_partials,
+                     unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+  const double alpha = *alpha_dev;
+  const double nalpha = -alpha;
+  double acc = 0.0;
+  const int npair = n >> 1;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+    const long long e = 2 * (long long)i;
+    const double2 pv = ld_stream_f64x2(p + e);
+    const double2 av = ld_stream_f64x2(Ap + e);
+    double2 xv = *reinterpret_cast<const double2 *>(x + e);
+    double2 rv = *reinterpret_cast<const double2 *>(r + e);
+    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+    rv.x = __dadd_rn(rv.x, __dmul_rn(nalpha, av.x));
+    rv.y = __dadd_rn(rv.y, __dmul_rn(nalpha, av.y));
+    *reinterpret_cast<double2 *>(x + e) = xv;
+    *reinterpret_cast<double2 *>(r + e) = rv;
+    acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
+    acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int i = n - 1;
+    const double xn = __dadd_rn(x[i], __dmul_rn(alpha, p[i]));
+    const double rn = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
+    x[i] = xn;
+    r[i] = rn;
+    acc = __dadd_rn(acc, __dmul_rn(rn, rn));
+  }
+  const double total = block_sum(acc, smem);
+  publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
+}
+
+// ---- HPCCG.cpp:352-353 fused: r = b - Ap (waxpby alpha==1 branch, beta=-1) and r.r ------------------------
+__global__ void __launch_bounds__(kThreads)
+residual_dot_kernel(int n, const double *__restrict__ b, const double *__restrict__ Ap, double *__restrict__ r,
+                    double *partials, int total_partials, unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  double acc = 0.0;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const double rv = __dadd_rn(b[i], __dmul_rn(-1.0, Ap[i]));
+    r[i] = rv;
+    acc = __dadd_rn(acc, __dmul_rn(rv, rv));
+  }
+  const double total = block_sum(acc, smem);
+  publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
+}
+
+// ---- exchange_externals.cpp:103 -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+halo_pack_kernel(int count, const int *__restrict__ elements_to_send, const double *__restrict__ x,
+                 double *__restrict__ send_buffer, const CgState *st_check) {
+  if (st_check && st_check->active == 0) return;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads)
+    send_buffer[i] = x[elements_to_send[i]];
+}
+
+// ---- compute_residual.cpp:59-81 (local part): max |v1-v2| ---------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+max_abs_diff_kernel(int n, const double *__restrict__ v1, const double *__restrict__ v2, double *partials,
+                    int total_partials, unsigned *counter, double *out) {
+  __shared__ double smem[kThreads / 32];
+  __shared__ int s_last;
+  double m = 0.0;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const double d = fabs(v1[i] - v2[i]);
+    if (d > m) m = d;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) smem[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) m = fmax(m, smem[w]);
+    partials[blockIdx.x] = m;
+    __threadfence();
+    const unsigned ticket = atomicInc(counter, (unsigned)(total_partials - 1));
+    s_last = (ticket == (unsigned)(total_partials - 1));
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double g = 0.0;
+    for (int i = 0; i < total_partials; ++i) g = fmax(g, __ldcg(partials + i));
+    *out = g;
+  }
+}
+
+// ---- multi-rank scalar step: sum the gathered per-rank contributions in RANK ORDER ----------------------
+// (the order of oracle/mpi_shim's MPI_Allreduce; ddot.cpp:77-82), then the same finish action.
+__global__ void cg_scalar_kernel(const double *gathered, int nranks, FinishParams fp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (fp.check_active && fp.st->active == 0) return;
+  double g = gathered[0];
+  for (int r = 1; r < nranks; ++r) g = __dadd_rn(g, gathered[r]);
+  cg_finish(fp, g);
+}
+
+__global__ void cg_state_init_kernel(CgState *st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->rtrans = st->oldrtrans = st->alpha = st->neg_alpha = st->beta = st->pAp = st->normr = st->zero = st->local_sum = 0.0;
+    st->niters = 0;
+    st->active = 1;
+    st->counter = 0;
+    st->pad = 0;
+  }
+}
+
+// ---- generate_matrix.cpp:251-289 directly into the device ELL ----------------------------------------------
+// One thread per local row; slot j receives the j-th entry the reference's sz,sy,sx loop would store.
+__global__ void __launch_bounds__(kThreads)
+generate_ell_kernel(int nx, int ny, int nz, long long start_row, long long total_nrow, int stencil7, int slots,
+                    long long npad, const int *__restrict__ lower_map, const int *__restrict__ upper_map,
+                    double *__restrict__ vals, int *__restrict__ cols) {
+  const long long n = (long long)nx * ny * nz;
+  const long long plane = (long long)nx * ny;
+  for (long long row = (long long)blockIdx.x * kThreads + threadIdx.x; row < npad; row += (long long)gridDim.x * kThreads) {
+    int j = 0;
+    if (row < n) {
+      const int iz = (int)(row / plane);
+      const int rem = (int)(row - (long long)iz * plane);
+      const int iy = rem / nx, ix = rem - iy * nx;
+      const long long currow = start_row + row;
+      for (int sz = -1; sz <= 1; ++sz)
+        for (int sy = -1; sy <= 1; ++sy)
+          for (int sx = -1; sx <= 1; ++sx) {
+            const long long curcol = currow + sz * plane + sy * nx + sx;
+            if (ix + sx >= 0 && ix + sx < nx && iy + sy >= 0 && iy + sy < ny && curcol >= 0 && curcol < total_nrow) {
+              if (!stencil7 || sz * sz + sy * sy + sx * sx <= 1) {
+                int lc;
+                const int zz = iz + sz;
+                const int q = (iy + sy) * nx + (ix + sx);
+                if (zz < 0) lc = lower_map[q];
+                else if (zz >= nz) lc = upper_map[q];
+                else lc = (int)(curcol - start_row);
+                vals[(long long)j * npad + row] = (curcol == currow) ? 27.0 : -1.0;
+                cols[(long long)j * npad + row] = lc;
+                ++j;
+              }
+            }
+          }
+    }
+    for (; j < slots; ++j) {
+      vals[(long long)j * npad + row] = 0.0;
+      cols[(long long)j * npad + row] = -1;
+    }
+  }
+}
+
+// b = 27 - (nnz_row - 1), x = 0, xexact = 1 (generate_matrix.cpp:284-286) for device-only generation.
+__global__ void __launch_bounds__(kThreads)
+generate_vectors_kernel(int n, int slots, long long npad, const int *__restrict__ cols, double *x, double *b,
+                        double *xexact) {
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    int nnzrow = 0;
+    for (int j = 0; j < slots; ++j) nnzrow += (cols[(long long)j * npad + i] >= 0) ? 1 : 0;
+    if (x) x[i] = 0.0;
+    if (b) b[i] = 27.0 - ((double)(nnzrow - 1));
+    if (xexact) xexact[i] = 1.0;
+  }
+}
+
+}  // namespace hpccg

@@ -71,7 +71,7 @@ build_variant() {  # name flags tus sed
     "$CXX" $flags -c -o "$OUT/$name/mpi_shim.o" mpi_shim/mpi_shim.cpp
   fi
   # shellcheck disable=SC2086
-  "$CXX" -shared $flags -o "$lib" "$OUT/$name"/*.o -lpthread -lm
+  "$CXX" -shared -Wl,-Bsymbolic $flags -o "$lib" "$OUT/$name"/*.o -lpthread -lm
   rm -rf "$OUT/$name"
   echo "built $lib"
 }

@@ -20,21 +20,38 @@ _PD = C.POINTER(C.c_double)
 _PPD = C.POINTER(_PD)
 
 
+def _path(variant: str) -> Path:
+    # "oracle" = the C restatement (hpccg_oracle.c); the rest = the real reference
+    return _REFDIR / ("libhpccg_oracle.so" if variant == "oracle" else f"libhpccg_ref_{variant}.so")
+
+
 def available(variant: str = "serial") -> bool:
-    return (_REFDIR / f"libhpccg_ref_{variant}.so").exists()
+    return _path(variant).exists()
 
 
-_libs: dict[str, C.CDLL] = {}
+class _Prefixed:
+    """Maps lib.ref_foo onto orc_foo for the C restatement, which has the same C-ABI."""
+
+    def __init__(self, cdll, prefix):
+        self._cdll, self._prefix = cdll, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("ref_"):
+            name = self._prefix + name[4:]
+        return getattr(self._cdll, name)
 
 
-def _lib(variant: str) -> C.CDLL:
+_libs: dict = {}
+
+
+def _lib(variant: str):
     if variant in _libs:
         return _libs[variant]
-    path = _REFDIR / f"libhpccg_ref_{variant}.so"
+    path = _path(variant)
     if not path.exists():
-        raise FileNotFoundError(f"{path} missing: run oracle/build.sh where /root/reference exists")
-    # RTLD_LOCAL: the three variants export the same reference symbols.
-    lib = C.CDLL(str(path), mode=os.RTLD_LOCAL | os.RTLD_NOW)
+        raise FileNotFoundError(f"{path} missing: run oracle/build.sh (the ref_* variants need /root/reference)")
+    # RTLD_LOCAL: the three reference variants export the same symbols.
+    lib = _Prefixed(C.CDLL(str(path), mode=os.RTLD_LOCAL | os.RTLD_NOW), "orc_" if variant == "oracle" else "ref_")
     lib.ref_create.restype = C.c_void_p
     lib.ref_create.argtypes = [C.c_int] * 5
     lib.ref_destroy.argtypes = [C.c_void_p]
@@ -48,8 +65,9 @@ def _lib(variant: str) -> C.CDLL:
     lib.ref_waxpby.argtypes = [C.c_int, C.c_double, _PD, C.c_double, _PD, _PD]
     lib.ref_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _PD, C.POINTER(C.c_int), _PD, _PD, _PPD]
     lib.ref_compute_residual.argtypes = [C.c_void_p, _PPD, _PD]
-    lib.ref_yaml_report.argtypes = [C.c_int] * 4 + [C.c_double, _PD, C.c_double, C.c_double, C.c_int, C.c_int, _PD,
-                                                    C.c_char_p, C.c_int]
+    if variant != "oracle":
+        lib.ref_yaml_report.argtypes = [C.c_int] * 4 + [C.c_double, _PD, C.c_double, C.c_double, C.c_int, C.c_int,
+                                                        _PD, C.c_char_p, C.c_int]
     _libs[variant] = lib
     return lib
 
