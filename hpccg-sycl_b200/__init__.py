@@ -28,7 +28,7 @@ from . import _capi
 from ._capi import HpccgError, check, lib
 
 __all__ = [
-    "HpccgError", "Matrix", "DeviceMatrix", "set_rank", "get_rank", "set_options", "generate_matrix",
+    "HpccgError", "Matrix", "DeviceMatrix", "set_rank", "get_rank", "set_options", "set_print", "generate_matrix",
     "make_local_matrix", "HPCCG", "HPC_sparsemv", "ddot", "waxpby", "exchange_externals", "compute_residual",
     "yaml_report", "run_local_world", "launch_count", "dev",
 ]
@@ -169,6 +169,11 @@ class Matrix:
             self.x = self.b = self.xexact = None
 
 
+def set_print(on: bool) -> None:
+    """Residual lines of HPCCG.cpp:356,372-373 on rank 0 (default on, like the reference)."""
+    check(lib.hpccg_api_set_print(1 if on else 0))
+
+
 def generate_matrix(nx: int, ny: int, nz: int) -> Matrix:
     """generate_matrix.cpp:196-307; returns the matrix with its x (zeros), b (= A*1) and xexact (ones)."""
     A = C.c_void_p()
@@ -297,7 +302,7 @@ class _Dev:
                  want_times=False):
         niters, normr, loop_ms = C.c_int(), C.c_double(), C.c_double()
         hist = np.full(max(max_iter, 1), np.nan) if want_hist else None
-        times = np.zeros(7) if want_times else None
+        times = np.zeros(16) if want_times else None
         check(lib.hpccg_dev_cg_solve(m.handle, _ptr(b), _ptr(x), max_iter, tolerance, C.byref(niters), C.byref(normr),
                                      _ptr(hist), _ptr(times), C.byref(loop_ms), flags, _stream(stream)),
               "hpccg_dev_cg_solve")

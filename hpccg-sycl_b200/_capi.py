@@ -63,6 +63,7 @@ SIGNATURES = {
     "hpccg_dev_cg_solve_group": (C.c_int, [C.c_int, PVP, PVP, PVP, C.c_int, C.c_double, PI, PD, VP, PD, C.c_int, VP]),
     "hpccg_launch_count": (C.c_longlong, []),
     "hpccg_api_set_options": (C.c_int, [C.c_int, C.c_int]),
+    "hpccg_api_set_print": (C.c_int, [C.c_int]),
     "hpccg_api_generate_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, PVP, C.POINTER(PD), C.POINTER(PD), C.POINTER(PD)]),
     "hpccg_api_make_local_matrix": (C.c_int, [VP]),
     "hpccg_api_HPCCG": (C.c_int, [VP, VP, VP, C.c_int, C.c_double, PI, PD, PD]),

@@ -17,6 +17,7 @@ struct RankContext {
   // generate_matrix options the reference fixes at compile time
   int stencil = 27;     // generate_matrix.cpp:219
   int host_arrays = 1;  // 0: device-only generation
+  int print_residuals = 1;  // HPCCG() prints the reference's residual lines on rank 0
 };
 
 RankContext &ctx();  // thread-local

@@ -675,7 +675,7 @@ int hpccg_dev_max_abs_diff(int n, const double *v1, const double *v2, double *re
 // ================================================================================================
 namespace hpccg {
 
-enum TimerCat { T_DDOT = 1, T_WAXPBY = 2, T_SPMV = 3, T_ALLRED = 4, T_EXCH = 5, T_FUSED_SPMV = 8, T_FUSED_UPD = 9 };
+enum TimerCat { T_DDOT = 1, T_WAXPBY = 2, T_SPMV = 3, T_ALLRED = 4, T_EXCH = 5, T_FUSED_SPMV = 8, T_FUSED_UPD = 9, T_PUPD = 10 };
 
 // Pairs of CUDA events around launches, accumulated per category after the solve.
 struct EventTimers {
@@ -919,7 +919,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       if (multi) HPCCG_TRY(finish_multi(FIN_RR, k - 1, 0, true));
     }
     // p = r (k==1, HPCCG.cpp:362) or p = r + beta p (:369)
-    timers.tick(T_WAXPBY);
+    timers.tick(T_PUPD);
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
       if (k == 1) HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
@@ -1022,8 +1022,13 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     times[1] = acc[T_DDOT] + acc[T_FUSED_SPMV] * (16.0 / 356.0) + acc[T_FUSED_UPD] * (8.0 / 56.0);
     times[2] = acc[T_WAXPBY] + acc[T_FUSED_UPD] * (48.0 / 56.0);
     times[3] = acc[T_SPMV] + acc[T_FUSED_SPMV] * (340.0 / 356.0);
+    times[2] += acc[T_PUPD];
     times[4] = acc[T_ALLRED] + t4_host;
     times[5] = acc[T_EXCH];
+    times[7] = acc[T_FUSED_SPMV];
+    times[8] = acc[T_FUSED_UPD];
+    times[9] = acc[T_PUPD];
+    times[10] = hs.niters;
   }
   return 0;
 }

@@ -699,7 +699,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   }
   const int iters = std::max(max_iter, 1);
   t_last_history.assign(iters, std::nan(""));
-  double local_times[7] = {0, 0, 0, 0, 0, 0, 0};
+  double local_times[16] = {0};
   int flags = HPCCG_SOLVE_TIMERS;
   if (const char *e = std::getenv("HPCCG_B200_UNFUSED"))
     if (e[0] == '1') flags |= HPCCG_SOLVE_UNFUSED;
@@ -711,7 +711,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   normr = nr;
 
   // Residual lines of HPCCG.cpp:356,372-373, printed after the device-resident loop has finished.
-  if (ctx().rank == 0) {
+  if (ctx().rank == 0 && ctx().print_residuals) {
     int print_freq = max_iter / 10;  // HPCCG.cpp:342-344
     if (print_freq > 50) print_freq = 50;
     if (print_freq < 1) print_freq = 1;
@@ -735,6 +735,11 @@ int hpccg_api_set_options(int stencil, int host_arrays) {
   if (stencil != 27 && stencil != 7) return fail(HPCCG_ERR_ARG, "stencil must be 27 or 7");
   ctx().stencil = stencil;
   ctx().host_arrays = host_arrays ? 1 : 0;
+  return 0;
+}
+
+int hpccg_api_set_print(int on) {
+  ctx().print_residuals = on ? 1 : 0;
   return 0;
 }
 

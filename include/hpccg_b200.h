@@ -129,7 +129,9 @@ int hpccg_dev_max_abs_diff(int n, const double *v1, const double *v2, double *re
  *   HPCCG.cpp:358 is honoured by a device flag that turns the remaining launches into no-ops.
  *   hist_host (may be NULL): max_iter doubles, [0] = initial residual, [k] = normr of iteration k
  *   (what HPCCG.cpp:356,372-373 would print with print_freq = 1), NaN where no iteration ran.
- *   times (may be NULL): 7 doubles as HPCCG.cpp:389-399 (see DESIGN.md for the fused attribution);
+ *   times (may be NULL): 16 doubles; [0..6] as HPCCG.cpp:389-399 (see DESIGN.md for the fused attribution),
+ *   [7] seconds in the fused SpMV+p.Ap kernel, [8] in the fused x/r-update+r.r kernel, [9] in the p-update
+ *   kernel, [10] number of timed iterations (raw CUDA-event sums; need HPCCG_SOLVE_TIMERS);
  *   loop_ms (may be NULL): CUDA-event time of iterations 1..niters only.
  *   flags: HPCCG_SOLVE_* bits.
  * With an NCCL communicator (hpccg_nccl_init) and ctx size > 1 this is one rank of a z-stacked job.
@@ -158,6 +160,8 @@ long long hpccg_launch_count(void);
 /* Options the reference fixes at compile time: stencil (generate_matrix.cpp:219, 27 or 7) and whether
  * generate_matrix materialises the host row arrays (0 = device-only, needed beyond 430^3). Thread-local. */
 int hpccg_api_set_options(int stencil, int host_arrays);
+/* HPCCG() prints "Initial Residual" / "Iteration = k   Residual" on rank 0 like HPCCG.cpp:356,372-373; 0 silences it. */
+int hpccg_api_set_print(int on);
 /* generate_matrix.hpp:58 */
 int hpccg_api_generate_matrix(int nx, int ny, int nz, void **A, double **x, double **b, double **xexact);
 /* make_local_matrix.hpp:48 */
