@@ -1,0 +1,42 @@
+"""-m gpu: the reference-compatible command-line driver (hpccg-sycl_b200/apps/test_HPCCG.cpp):
+`test_HPCCG nx ny nz` prints the reference's residual lines and YAML keys (main.cpp:230-304, out.txt) and writes
+./hpccg-1.0_<timestamp>.yaml (YAML_Doc.cpp:49-70)."""
+import os
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+EXE = ROOT / "hpccg-sycl_b200" / "lib" / "test_HPCCG"
+
+
+def run(args, cwd):
+    return subprocess.run([str(EXE), *args], cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+def test_cli_matches_out_txt(H, cuda, tmp_path):
+    """out.txt of the reference: 10x10x10 serial, 149 iterations, 'Initial Residual = 258.24',
+    'Iteration = 15   Residual = 2.15402e-06', FLOP counts 9.536e+06 / 596000 / 894000 / 8.046e+06."""
+    res = run(["10", "10", "10", "--check"], tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = res.stdout
+    assert "Initial Residual = 258.24\n" in out
+    assert "Iteration = 15   Residual = 2.15402e-06\n" in out
+    assert "Number of iterations: 149\n" in out
+    for line in ("Mini-Application Name: hpccg", "Mini-Application Version: 1.0", "  nx: 10", "  Total   : 9.536e+06",
+                 "  DDOT    : 596000", "  WAXPBY  : 894000", "  SPARSEMV: 8.046e+06", "Time Summary: ", "MFLOPS Summary: "):
+        assert line + "\n" in out, line
+    m = re.search(r"Difference between computed and exact: (\S+)", out)
+    assert m and float(m.group(1)) <= 1e-12
+    assert [f for f in os.listdir(tmp_path) if re.fullmatch(r"hpccg-1\.0_\d{4}_\d\d_\d\d__\d\d_\d\d_\d\d\.yaml", f)]
+
+
+def test_cli_7pt_device_only_and_usage(H, cuda, tmp_path):
+    res = run(["32", "32", "32", "--stencil", "7", "--device-only", "--iters", "40", "--check"], tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Number of iterations: 39\n" in res.stdout and "Stencil points: 7" in res.stdout
+    assert run([], tmp_path).returncode == 1
+    assert "Usage:" in run(["4", "4"], tmp_path).stderr
