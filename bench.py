@@ -405,7 +405,8 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
     peak, peak_src = measured_peak()
     k = main["kernels"]["spmv_dot"]
     roofline = {"bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": (k["gbs"] or 0) / peak,
-                "traffic": ncu_traffic(w["name"]), "kernel": f"spmv_ell_kernel<{main['slots']},2,true> (fused SpMV + p.Ap)",
+                "traffic": ncu_traffic(w["name"]), "kernel": (f"spmv_sell_tma_kernel<{main['slots']},...,true>" if main["slots"] in (7, 27) and os.environ.get("HPCCG_B200_SPMV") != "reg"
+                           else f"spmv_ell_kernel<{main['slots']},2,true>") + " (fused SpMV + p.Ap)",
                 "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"], "peak_source": peak_src,
                 "loop": {"bytes_per_iteration": main["kernels"]["iteration"]["bytes"],
                          "ms_per_iteration": main["kernels"]["iteration"]["ms"], "achieved": main["kernels"]["iteration"]["gbs"],

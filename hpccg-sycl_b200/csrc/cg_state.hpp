@@ -5,6 +5,19 @@ namespace hpccg {
 
 constexpr int kThreads = 256;          // threads per block for every kernel here
 constexpr int kMaxPartials = 8192;     // capacity of the per-matrix block-partial array
+constexpr int kSliceRows = 128;        // C of the SELL-C layout: rows per slice
+constexpr int kRowPad = 512;           // local_nrow is padded to a multiple of this (4 slices)
+
+// SELL-C (C = kSliceRows, sigma = 1: rows keep the reference's order) addressing of the matrix arrays:
+// slice s = row / C holds its `slots` x C entries contiguously, slot-major inside the slice, so that
+//   * a warp reading one slot of 32/64 consecutive rows touches one contiguous 256/512-byte segment, and
+//   * a whole slice (or k consecutive slices) is ONE contiguous block -- what a TMA bulk copy moves.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline long long sell_offset(long long row, int slot, int slots) {
+  return ((row / kSliceRows) * slots + slot) * kSliceRows + (row % kSliceRows);
+}
 
 // Device-resident scalars of one CG solve (HPCCG.cpp:331-333,366-382 keep these on the host).
 struct CgState {

@@ -2,6 +2,7 @@
 // launchers and the device-resident CG loop.  There is NO CPU fallback in this file: every operation is
 // a CUDA kernel launch, and every CUDA error is returned to the caller.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <atomic>
@@ -195,11 +196,101 @@ static int spmv_max_grid(int slots) {
 }
 
 template <bool DOT>
-static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
-                       int total_partials, const FinishParams &fp, cudaStream_t s) {
+static int launch_spmv_reg(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                           int total_partials, const FinishParams &fp, cudaStream_t s) {
   if (m->slots == 27) return launch_spmv_t<27, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
   if (m->slots == 7) return launch_spmv_t<7, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
   return launch_spmv_t<0, 2, DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
+}
+
+// ---- TMA path (27 and 7 slots): stages of SPS slices, persistent CTAs ------------------------------------
+// HPCCG_B200_SPMV=reg forces the register path (A/B measurements).
+static bool use_tma_path(int slots) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = std::getenv("HPCCG_B200_SPMV");
+    mode = (e && std::string(e) == "reg") ? 0 : 1;
+  }
+  return mode == 1 && (slots == 27 || slots == 7);
+}
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static int tma_ctas_per_sm() {
+  static int cached = 0;
+  if (cached) return cached;
+  using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
+  auto kern = spmv_sell_tma_kernel<SLOTS, SPS, NSTAGES, DOT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kRows, Cfg::kSmemBytes) != cudaSuccess || per_sm < 1)
+    return -1;
+  cached = per_sm;
+  return cached;
+}
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static SpmvPlan plan_tma(int row_begin, int row_end) {
+  SpmvPlan p{row_begin, row_end, 0, 0};
+  if (row_end <= row_begin) return p;
+  constexpr int rows = SPS * kSliceRows;
+  const int sb = row_begin / rows, se = (row_end + rows - 1) / rows;
+  p.tiles = se - sb;
+  const int per_sm = tma_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>();
+  p.grid = std::min(p.tiles, std::max(1, per_sm) * device_info().sm_count);
+  return p;
+}
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static int launch_tma_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                        int total_partials, const FinishParams &fp, cudaStream_t s) {
+  if (pl.grid == 0) return 0;
+  using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
+  if (tma_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>() < 1)
+    return fail(HPCCG_ERR_STATE, "TMA SpMV kernel cannot be resident (%d bytes of shared memory)", Cfg::kSmemBytes);
+  constexpr int rows = Cfg::kRows;
+  const int sb = pl.row_begin / rows;
+  spmv_sell_tma_kernel<SLOTS, SPS, NSTAGES, DOT><<<pl.grid, rows, Cfg::kSmemBytes, s>>>(
+      m->vals, m->cols, x, y, pl.row_begin, pl.row_end, sb, sb + pl.tiles, m->partials, partial_offset, total_partials,
+      &m->state->counter, fp);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Stage shapes.  27 slots: 2 slices (256 rows, 81 KB) x 2 stages, 1 CTA/SM (variant 0, default);
+// 1 slice x 2 stages, 2 CTAs/SM (variant 1); 1 slice x 5 stages, 1 CTA/SM (variant 2) -- HPCCG_B200_TMA_VARIANT
+// selects, for the A/B measurements recorded in DESIGN.md.  7 slots: 2 slices (21 KB) x 4 stages, 2 CTAs/SM.
+static int tma_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = std::getenv("HPCCG_B200_TMA_VARIANT");
+    v = e ? std::atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
+}
+
+#define HPCCG_TMA_DISPATCH(FN, DOT, ...)                                   \
+  do {                                                                     \
+    if (m->slots == 7) return FN<7, 2, 4, DOT>(__VA_ARGS__);               \
+    switch (tma_variant()) {                                               \
+      case 1: return FN<27, 1, 2, DOT>(__VA_ARGS__);                       \
+      case 2: return FN<27, 1, 5, DOT>(__VA_ARGS__);                       \
+      default: return FN<27, 2, 2, DOT>(__VA_ARGS__);                      \
+    }                                                                      \
+  } while (0)
+
+template <bool DOT>
+static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end) {
+  if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(plan_tma, DOT, row_begin, row_end);
+  return plan_range<2>(row_begin, row_end, spmv_max_grid<DOT>(m->slots));
+}
+
+template <bool DOT>
+static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                       int total_partials, const FinishParams &fp, cudaStream_t s) {
+  if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s);
+  return launch_spmv_reg<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
@@ -209,10 +300,10 @@ static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool
                      cudaStream_t s) {
   if (!aligned16(x) || !aligned16(y)) return fail(HPCCG_ERR_ARG, "SpMV vectors must be 16-byte aligned");
   if (dot) {
-    SpmvPlan pl = plan_range<2>(0, m->n, spmv_max_grid<true>(m->slots));
+    SpmvPlan pl = plan_spmv<true>(m, 0, m->n);
     return launch_spmv<true>(m, x, y, pl, 0, pl.grid, fp, s);
   }
-  SpmvPlan pl = plan_range<2>(0, m->n, spmv_max_grid<false>(m->slots));
+  SpmvPlan pl = plan_spmv<false>(m, 0, m->n);
   return launch_spmv<false>(m, x, y, pl, 0, 0, fp, s);
 }
 
@@ -321,7 +412,7 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
   m->n = n;
   m->ncol = local_ncol;
   m->slots = slots;
-  m->npad = round_up(n, 512);
+  m->npad = round_up(n, kRowPad);
   // halo-touching rows: leading run [0,a) and trailing run [b,n); a row in the first half extends a,
   // one in the second half lowers b
   int a = 0, b = n;
@@ -363,8 +454,9 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
     return rc;
   }
 
-  // Repack rows into column-major ELL through two pinned staging buffers and copy with 2-D memcpys.
-  const int chunk = (int)std::min<long long>(m->npad, 1 << 18);  // rows per staging chunk
+  // Repack rows into the SELL-C layout through two pinned staging buffers.  A chunk of whole slices is one
+  // contiguous block of the device arrays, so each chunk is two plain 1-D copies.
+  const int chunk = (int)std::min<long long>(m->npad, 1 << 18);  // rows per staging chunk (a multiple of kRowPad)
   double *hv[2] = {nullptr, nullptr};
   int *hc[2] = {nullptr, nullptr};
   cudaStream_t cs = nullptr;
@@ -413,20 +505,20 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
             ci = ptr_to_inds_in_row[row];
           }
           for (int j = 0; j < nnz; ++j) {
-            sv[(size_t)j * chunk + i] = cv[j];
-            sc[(size_t)j * chunk + i] = ci[j];
+            const long long o = sell_offset(i, j, slots);  // chunk-relative: r0 is slice-aligned
+            sv[o] = cv[j];
+            sc[o] = ci[j];
           }
           for (int j = nnz; j < slots; ++j) {
-            sv[(size_t)j * chunk + i] = 0.0;
-            sc[(size_t)j * chunk + i] = -1;
+            const long long o = sell_offset(i, j, slots);
+            sv[o] = 0.0;
+            sc[o] = -1;
           }
         }
       });
     for (auto &t : th) t.join();
-    HPCCG_CUDA_CLEAN(cudaMemcpy2DAsync(m->vals + r0, sizeof(double) * m->npad, sv, sizeof(double) * chunk,
-                                       sizeof(double) * rows, slots, cudaMemcpyHostToDevice, cs));
-    HPCCG_CUDA_CLEAN(cudaMemcpy2DAsync(m->cols + r0, sizeof(int) * m->npad, sc, sizeof(int) * chunk, sizeof(int) * rows,
-                                       slots, cudaMemcpyHostToDevice, cs));
+    HPCCG_CUDA_CLEAN(cudaMemcpyAsync(m->vals + r0 * slots, sv, sizeof(double) * (size_t)rows * slots, cudaMemcpyHostToDevice, cs));
+    HPCCG_CUDA_CLEAN(cudaMemcpyAsync(m->cols + r0 * slots, sc, sizeof(int) * (size_t)rows * slots, cudaMemcpyHostToDevice, cs));
     HPCCG_CUDA_CLEAN(cudaEventRecord(ev[buf], cs));
   }
   HPCCG_CUDA_CLEAN(cudaStreamSynchronize(cs));
@@ -463,7 +555,7 @@ int hpccg_dev_matrix_generate(int nx, int ny, int nz, int rank, int size, int st
   };
   const int cx = span(nx, false, false), cy = span(ny, false, false), cz = span(nz, has_lower, has_upper);
   m->slots = stencil == 27 ? cx * cy * cz : 1 + (cx - 1) + (cy - 1) + (cz - 1);
-  m->npad = round_up(n, 512);
+  m->npad = round_up(n, kRowPad);
   int a = has_lower ? (int)plane : 0, b = has_upper ? (int)(n - plane) : (int)n;
   if (a > b) a = b = (int)n;
   m->interior_begin = a;
@@ -566,8 +658,20 @@ int hpccg_dev_matrix_info(const hpccg_dev_matrix *m, int *local_nrow, int *local
 
 int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int *cols_host) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
-  if (vals_host) HPCCG_CUDA(cudaMemcpy(vals_host, m->vals, sizeof(double) * (size_t)m->slots * m->npad, cudaMemcpyDeviceToHost));
-  if (cols_host) HPCCG_CUDA(cudaMemcpy(cols_host, m->cols, sizeof(int) * (size_t)m->slots * m->npad, cudaMemcpyDeviceToHost));
+  // The device arrays are SELL-C; the caller receives the canonical column-major [slots][padded_rows] view.
+  const size_t total = (size_t)m->slots * m->npad;
+  if (vals_host) {
+    std::vector<double> tmp(total);
+    HPCCG_CUDA(cudaMemcpy(tmp.data(), m->vals, sizeof(double) * total, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < m->slots; ++j)
+      for (long long r = 0; r < m->npad; ++r) vals_host[(size_t)j * m->npad + r] = tmp[sell_offset(r, j, m->slots)];
+  }
+  if (cols_host) {
+    std::vector<int> tmp(total);
+    HPCCG_CUDA(cudaMemcpy(tmp.data(), m->cols, sizeof(int) * total, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < m->slots; ++j)
+      for (long long r = 0; r < m->npad; ++r) cols_host[(size_t)j * m->npad + r] = tmp[sell_offset(r, j, m->slots)];
+  }
   return 0;
 }
 
@@ -934,10 +1038,9 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       HPCCG_CUDA(cudaStreamWaitEvent(m->comm_stream, m->ev_p_ready, 0));
       HPCCG_TRY(exchange_halo(rk, R, true, pv.data(), chk.data(), m->comm_stream));
       HPCCG_CUDA(cudaEventRecord(m->ev_halo_done, m->comm_stream));
-      const int maxg = spmv_max_grid<true>(m->slots);
-      SpmvPlan pi = plan_range<2>(m->interior_begin, m->interior_end, maxg);
-      SpmvPlan pa = plan_range<2>(0, m->interior_begin, maxg);
-      SpmvPlan pb = plan_range<2>(m->interior_end, m->n, maxg);
+      SpmvPlan pi = plan_spmv<true>(m, m->interior_begin, m->interior_end);
+      SpmvPlan pa = plan_spmv<true>(m, 0, m->interior_begin);
+      SpmvPlan pb = plan_spmv<true>(m, m->interior_end, m->n);
       const int total = pi.grid + pa.grid + pb.grid;
       FinishParams fp = fp_for(FIN_PAP, 0, k, 0, true);
       timers.tick(T_FUSED_SPMV);

@@ -2,10 +2,13 @@
 //
 // All kernels are HBM-bandwidth bound (arithmetic intensity ~0.155 flop/B);
 // nothing here is a dense contraction, so no tensor cores.  Design rules applied:
-//   * column-major ELLPACK so that a warp reads 32 (or 64) consecutive rows of one slot:
-//     every matrix load is a fully coalesced 128-bit (vals) / 64-bit (cols) access;
-//   * the matrix stream is read once with ld.global.nc.L1::no_allocate so it does not evict the
-//     gathered vector from L1; the vector x is gathered through L1/L2 (__ldg);
+//   * SELL-C layout (C = 128 rows per slice, slot-major inside a slice, cg_state.hpp) so that a warp reads
+//     32 (or 64) consecutive rows of one slot -- every matrix load is a fully coalesced 128-bit (vals) /
+//     64-bit (cols) access -- and a slice is one contiguous block that a TMA bulk copy can move;
+//   * the main SpMV streams the matrix with cp.async.bulk (TMA) into a shared-memory ring guarded by
+//     mbarriers, so the bytes in flight per SM do not depend on registers or occupancy; the register-path
+//     SpMV reads it with ld.global.nc.L1::no_allocate; either way the matrix stream never enters L1, which
+//     is left to the gathered vector x (__ldg through L1/L2);
 //   * persistent grid-stride tiles, grid = a multiple of the SM count, so reductions have a small,
 //     fixed number of block partials and a deterministic two-pass finish;
 //   * products and sums use __dmul_rn/__dadd_rn (never contracted into FMA) in the reference's
@@ -123,9 +126,12 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* kThreads/3
 
 // Publishes this block's partial; the block that takes the last ticket sums all partials in index
 // order (fixed tree, independent of which block happens to be last) and runs the finish action.
-__device__ __forceinline__ void publish_and_finish(double block_total, double *partials, int partial_index,
-                                                   int total_partials, unsigned *counter, const FinishParams &fp,
-                                                   double *smem) {
+// NT = threads of the calling block; smem holds NT/32 doubles.  The order in which the partials are combined
+// depends only on (total_partials, NT), never on block scheduling.
+template <int NT>
+__device__ __forceinline__ void publish_and_finish_n(double block_total, double *partials, int partial_index,
+                                                     int total_partials, unsigned *counter, const FinishParams &fp,
+                                                     double *smem) {
   __shared__ int s_last;
   if (threadIdx.x == 0) {
     partials[partial_index] = block_total;
@@ -137,12 +143,25 @@ __device__ __forceinline__ void publish_and_finish(double block_total, double *p
   if (!s_last) return;
   __threadfence();
   double acc = 0.0;
-  for (int i = threadIdx.x; i < total_partials; i += kThreads) acc = __dadd_rn(acc, __ldcg(partials + i));
-  acc = block_sum(acc, smem);
-  if (threadIdx.x == 0) cg_finish(fp, acc);
+  for (int i = threadIdx.x; i < total_partials; i += NT) acc = __dadd_rn(acc, __ldcg(partials + i));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  acc = warp_sum(acc);
+  if (lane == 0) smem[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double r = (lane < NT / 32) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+    if (lane == 0) cg_finish(fp, r);
+  }
 }
 
-// ---- HPC_sparsemv.cpp:68-89 on column-major ELL -----------------------------------------------------
+__device__ __forceinline__ void publish_and_finish(double block_total, double *partials, int partial_index,
+                                                   int total_partials, unsigned *counter, const FinishParams &fp,
+                                                   double *smem) {
+  publish_and_finish_n<kThreads>(block_total, partials, partial_index, total_partials, counter, fp, smem);
+}
+
+// ---- HPC_sparsemv.cpp:68-89, register path (any slot count, any row range) -----------------------------
 // SLOTS > 0: compile-time slot count (27, 7), fully unrolled so all matrix loads of a row pair are in
 // flight before the first gather.  SLOTS == 0: run-time slot count.  RPT rows per thread (2 = 128-bit
 // value loads).  Rows [row_begin,row_end) are processed; tiles start at the even row below row_begin.
@@ -160,14 +179,16 @@ spmv_ell_kernel(const double *__restrict__ vals, const int *__restrict__ cols, l
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int r0 = base + tile * kTileRows + threadIdx.x * RPT;
     if (r0 >= row_end) continue;
+    // SELL-C addressing: both rows of a pair are in the same slice (r0 and C are even)
+    const long long off0 = (long long)(r0 / kSliceRows) * slots * kSliceRows + (r0 % kSliceRows);
     if (RPT == 2) {
       double s0 = 0.0, s1 = 0.0;
-      const double *vp = vals + r0;
-      const int *cp = cols + r0;
+      const double *vp = vals + off0;
+      const int *cp = cols + off0;
 #pragma unroll
       for (int j = 0; j < slots; ++j) {
-        const double2 v = ld_stream_f64x2(vp + (long long)j * npad);
-        const int2 c = ld_stream_s32x2(cp + (long long)j * npad);
+        const double2 v = ld_stream_f64x2(vp + j * kSliceRows);
+        const int2 c = ld_stream_s32x2(cp + j * kSliceRows);
         if (c.x >= 0) s0 = __dadd_rn(s0, __dmul_rn(v.x, __ldg(x + c.x)));
         if (c.y >= 0) s1 = __dadd_rn(s1, __dmul_rn(v.y, __ldg(x + c.y)));
       }
@@ -184,12 +205,12 @@ spmv_ell_kernel(const double *__restrict__ vals, const int *__restrict__ cols, l
       }
     } else {
       double s0 = 0.0;
-      const double *vp = vals + r0;
-      const int *cp = cols + r0;
+      const double *vp = vals + off0;
+      const int *cp = cols + off0;
 #pragma unroll
       for (int j = 0; j < slots; ++j) {
-        const double v = ld_stream_f64(vp + (long long)j * npad);
-        const int c = ld_stream_s32(cp + (long long)j * npad);
+        const double v = ld_stream_f64(vp + j * kSliceRows);
+        const int c = ld_stream_s32(cp + j * kSliceRows);
         if (c >= 0) s0 = __dadd_rn(s0, __dmul_rn(v, __ldg(x + c)));
       }
       y[r0] = s0;
@@ -199,6 +220,132 @@ spmv_ell_kernel(const double *__restrict__ vals, const int *__restrict__ cols, l
   if (DOT) {
     const double total = block_sum(dot, smem);
     publish_and_finish(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, smem);
+  }
+}
+
+// ---- HPC_sparsemv.cpp:68-89, TMA path: the main SpMV --------------------------------------------------------
+// One stage = SPS consecutive slices = one contiguous block of the vals array and one of the cols array,
+// fetched by a single elected thread with two cp.async.bulk (global -> shared, mbarrier complete_tx) and an L2
+// evict_first hint (the matrix is read once per SpMV; L2 is for the gathered vector).  NSTAGES stages form a ring:
+// while the CTA's SPS*128 threads (one row each) compute from stage i, stages i+1 .. i+NSTAGES-1 are in flight.
+// Row sums are accumulated in slot order with un-contracted mul/add, i.e. bit-identical to the register path.
+// Rows outside [row_begin,row_end) of a stage are computed but neither stored nor added to the dot product, so
+// row ranges need not be stage-aligned.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar,
+                                             unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+template <int SLOTS, int SPS, int NSTAGES>
+struct SpmvTmaCfg {
+  static constexpr int kRows = SPS * kSliceRows;            // rows per stage = threads per CTA
+  static constexpr int kValBytes = SLOTS * kRows * 8;
+  static constexpr int kColBytes = SLOTS * kRows * 4;
+  static constexpr int kSmemBytes = NSTAGES * (kValBytes + kColBytes) + NSTAGES * 8 + 64;
+};
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+__global__ void __launch_bounds__(SPS *kSliceRows, 1)
+spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ cols, const double *__restrict__ x,
+                     double *__restrict__ y, int row_begin, int row_end, int stage_begin, int stage_end, double *partials,
+                     int partial_offset, int total_partials, unsigned *counter, FinishParams fp) {
+  using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
+  constexpr int kRows = Cfg::kRows;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sv = reinterpret_cast<double *>(smem_raw);
+  int *sc = reinterpret_cast<int *>(smem_raw + NSTAGES * Cfg::kValBytes);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + NSTAGES * (Cfg::kValBytes + Cfg::kColBytes));
+  __shared__ double red[kRows / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+
+  const int tid = threadIdx.x;
+  // stages of this CTA: stage_begin + blockIdx.x + i * gridDim.x
+  const int first = stage_begin + blockIdx.x;
+  const int my_count = first < stage_end ? (stage_end - first + gridDim.x - 1) / gridDim.x : 0;
+  unsigned long long policy = 0;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  }
+  __syncthreads();
+  auto issue = [&](int i) {  // elected thread only
+    const int st = i % NSTAGES;
+    const long long stage = first + (long long)i * gridDim.x;
+    mbar_expect_tx(bars + st, Cfg::kValBytes + Cfg::kColBytes);
+    tma_bulk_g2s(sv + (size_t)st * SLOTS * kRows, vals + stage * SLOTS * kRows, Cfg::kValBytes, bars + st, policy);
+    tma_bulk_g2s(sc + (size_t)st * SLOTS * kRows, cols + stage * SLOTS * kRows, Cfg::kColBytes, bars + st, policy);
+  };
+  if (tid == 0)
+    for (int i = 0; i < NSTAGES && i < my_count; ++i) issue(i);
+
+  // thread -> (slice of the stage, row of the slice): shared-memory offset of slot j is soff + j * kSliceRows
+  const int soff = (tid / kSliceRows) * SLOTS * kSliceRows + (tid % kSliceRows);
+  double dot = 0.0;
+  for (int i = 0; i < my_count; ++i) {
+    const int st = i % NSTAGES;
+    mbar_wait(bars + st, (unsigned)(i / NSTAGES) & 1u);
+    const double *v = sv + (size_t)st * SLOTS * kRows + soff;
+    const int *c = sc + (size_t)st * SLOTS * kRows + soff;
+    int ci[SLOTS];
+    double xv[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) ci[j] = c[j * kSliceRows];
+    // all SLOTS gathers are issued back to back and unconditionally (a padding slot reads x[0] and is discarded
+    // below), so no predicate is live across the loads and the compiler keeps every gather of the row in flight
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) xv[j] = __ldg(x + max(ci[j], 0));
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+      const double t = __dadd_rn(sum, __dmul_rn(v[j * kSliceRows], xv[j]));
+      sum = ci[j] >= 0 ? t : sum;  // padding slots do not exist in the reference's row (HPC_sparsemv.cpp:83-86)
+    }
+    const int row = (first + i * (int)gridDim.x) * kRows + tid;
+    if (row >= row_begin && row < row_end) {
+      y[row] = sum;
+      if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + row), sum));
+    }
+    __syncthreads();  // every thread has read stage st: it may be overwritten
+    if (tid == 0 && i + NSTAGES < my_count) issue(i + NSTAGES);
+  }
+  if (DOT) {
+    // block reduction in a fixed order (warp shuffle tree, then warp 0 over the warp sums)
+    const int lane = tid & 31, warp = tid >> 5;
+    double w = warp_sum(dot);
+    if (lane == 0) red[warp] = w;
+    __syncthreads();
+    double total = 0.0;
+    if (warp == 0) {
+      total = lane < kRows / 32 ? red[lane] : 0.0;
+      total = warp_sum(total);
+    }
+    publish_and_finish_n<kRows>(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, red);
   }
 }
 
@@ -405,16 +552,18 @@ generate_ell_kernel(int nx, int ny, int nz, long long start_row, long long total
                 if (zz < 0) lc = lower_map[q];
                 else if (zz >= nz) lc = upper_map[q];
                 else lc = (int)(curcol - start_row);
-                vals[(long long)j * npad + row] = (curcol == currow) ? 27.0 : -1.0;
-                cols[(long long)j * npad + row] = lc;
+                const long long o = sell_offset(row, j, slots);
+                vals[o] = (curcol == currow) ? 27.0 : -1.0;
+                cols[o] = lc;
                 ++j;
               }
             }
           }
     }
     for (; j < slots; ++j) {
-      vals[(long long)j * npad + row] = 0.0;
-      cols[(long long)j * npad + row] = -1;
+      const long long o = sell_offset(row, j, slots);
+      vals[o] = 0.0;
+      cols[o] = -1;
     }
   }
 }
@@ -425,7 +574,7 @@ generate_vectors_kernel(int n, int slots, long long npad, const int *__restrict_
                         double *xexact) {
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
     int nnzrow = 0;
-    for (int j = 0; j < slots; ++j) nnzrow += (cols[(long long)j * npad + i] >= 0) ? 1 : 0;
+    for (int j = 0; j < slots; ++j) nnzrow += (cols[sell_offset(i, j, slots)] >= 0) ? 1 : 0;
     if (x) x[i] = 0.0;
     if (b) b[i] = 27.0 - ((double)(nnzrow - 1));
     if (xexact) xexact[i] = 1.0;

@@ -74,7 +74,7 @@ def full(tag, workload):
     if p.exists():
         traffic = json.loads(p.read_text())
     for r in rows[2:]:
-        if "spmv_ell_kernel" in r[idx["Kernel Name"]] and ", 1>" in r[idx["Kernel Name"]].split("(")[0]:
+        if "spmv_" in r[idx["Kernel Name"]] and ", 1>" in r[idx["Kernel Name"]].split("(")[0]:
             rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT_TO_BYTES[units[idx["dram__bytes_read.sum"]]]
             wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT_TO_BYTES[units[idx["dram__bytes_write.sum"]]]
             traffic[workload] = rd + wr
