@@ -36,4 +36,29 @@ struct CgState {
   unsigned pad;
 };
 
+// ---- peer-memory communication (multi-GPU, one process per GPU; NVLink / NVSwitch P2P) ------------------------
+// Replaces MPI_Allreduce (ddot.cpp:79-80) and MPI_Irecv/Send/Wait (exchange_externals.cpp:87-126) INSIDE the kernels:
+// every rank owns a Mailbox in its HBM that its peers write through IPC-mapped pointers.
+constexpr int kMaxRanks = 16;     // ranks of one NVSwitch domain
+constexpr int kMaxPeerNb = 4;     // halo neighbours served over peer memory (z-slabs have <= 2)
+constexpr int kMailSlots = 4;     // ring of reduction slots (a rank can be at most one reduction ahead)
+
+struct Mailbox {
+  double value[kMailSlots][kMaxRanks];            // value[slot][r]: rank r's contribution to reduction `seq`
+  unsigned long long seq[kMailSlots][kMaxRanks];  // stamp written after the value (release, system scope)
+  unsigned long long halo_seq[kMaxPeerNb];        // halo_seq[i]: exchange number of the last plane my neighbour i delivered
+};
+
+struct PeerLink {
+  int rank, size, nnb, error;
+  Mailbox *box[kMaxRanks];                  // box[rank] is this rank's own mailbox (local pointer), the rest are peers'
+  double *nb_dst[kMaxPeerNb];               // where my send segment i lands inside neighbour i's p vector
+  unsigned long long *nb_flag[kMaxPeerNb];  // neighbour i's halo_seq entry for me
+  int seg_start[kMaxPeerNb + 1];            // segment boundaries of elements_to_send
+  unsigned long long reduce_seq;            // device-local counters; identical on every rank by construction
+  unsigned long long halo_seq;
+  unsigned int ticket;
+  unsigned int pad;
+};
+
 }  // namespace hpccg

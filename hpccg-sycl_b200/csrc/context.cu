@@ -3,12 +3,15 @@
 #include <nccl.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.hpp"
 #include "context.hpp"
+#include "device_matrix.hpp"
 
 namespace hpccg {
 
@@ -146,6 +149,136 @@ int nccl_halo_exchange(const double *send_buffer, const int *send_length, double
     sp += send_length[i];
   }
   HPCCG_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+int nccl_allgather_host(const void *send, long long nbytes, void *recv) {
+  if (!g_comm) return fail(HPCCG_ERR_STATE, "no NCCL communicator");
+  char *d = nullptr;
+  HPCCG_CUDA(cudaMalloc(&d, (size_t)nbytes * (g_comm_size + 1)));
+  cudaError_t e = cudaMemcpy(d, send, (size_t)nbytes, cudaMemcpyHostToDevice);
+  int rc = 0;
+  if (e != cudaSuccess) rc = fail_cuda(e, "allgather staging", __FILE__, __LINE__);
+  if (!rc) {
+    ncclResult_t r = g_nccl.AllGather(d, d + nbytes, (size_t)nbytes, ncclChar, g_comm, nullptr);
+    if (r != ncclSuccess) rc = fail_nccl(r, "ncclAllGather (bytes)");
+  }
+  if (!rc) {
+    e = cudaMemcpy(recv, d + nbytes, (size_t)nbytes * g_comm_size, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail_cuda(e, "allgather readback", __FILE__, __LINE__);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+// ---- peer-memory link -----------------------------------------------------------------------------------------
+struct PeerCard {  // what every rank publishes about itself
+  cudaIpcMemHandle_t mailbox, p;
+  int ok;                 // this rank could allocate / export
+  int n, nnb;
+  int neighbors[kMaxPeerNb], recv_length[kMaxPeerNb], send_length[kMaxPeerNb];
+};
+
+void peer_link_destroy(hpccg_dev_matrix *m) {
+  for (void *p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  m->ipc_opened.clear();
+  if (m->peer_link) cudaFree(m->peer_link);
+  if (m->mailbox) cudaFree(m->mailbox);
+  m->peer_link = nullptr;
+  m->mailbox = nullptr;
+}
+
+int peer_link_create(hpccg_dev_matrix *m) {
+  if (m->peer_tried) return 0;
+  m->peer_tried = 1;
+  const int R = g_comm_size, me = g_comm_rank;
+  PeerCard mine;
+  std::memset(&mine, 0, sizeof mine);
+  mine.ok = (R <= kMaxRanks && m->num_neighbors <= kMaxPeerNb && m->p != nullptr) ? 1 : 0;
+  if (const char *e = std::getenv("HPCCG_B200_COMM"))
+    if (std::string(e) == "nccl") mine.ok = 0;  // A/B switch: NCCL send/recv + gathers
+  if (mine.ok) {
+    if (cudaMalloc(&m->mailbox, sizeof(Mailbox)) != cudaSuccess || cudaMemset(m->mailbox, 0, sizeof(Mailbox)) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.mailbox, m->mailbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.p, m->p) != cudaSuccess) {
+      cudaGetLastError();
+      mine.ok = 0;
+    }
+  }
+  mine.n = m->n;
+  mine.nnb = m->num_neighbors;
+  for (int i = 0; i < m->num_neighbors && i < kMaxPeerNb; ++i) {
+    mine.neighbors[i] = m->neighbors[i];
+    mine.recv_length[i] = m->recv_length[i];
+    mine.send_length[i] = m->send_length[i];
+  }
+  HPCCG_CUDA(cudaDeviceSynchronize());  // the memset above is complete before any peer can write
+  std::vector<PeerCard> cards(R);
+  HPCCG_TRY(nccl_allgather_host(&mine, sizeof mine, cards.data()));
+  bool all_ok = true;
+  for (const PeerCard &c : cards) all_ok = all_ok && c.ok;
+
+  PeerLink h;
+  std::memset(&h, 0, sizeof h);
+  h.rank = me;
+  h.size = R;
+  h.nnb = m->num_neighbors;
+  std::vector<void *> p_base(R, nullptr);
+  if (all_ok) {
+    for (int r = 0; r < R && all_ok; ++r) {
+      if (r == me) {
+        h.box[r] = m->mailbox;
+        continue;
+      }
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, cards[r].mailbox, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        all_ok = false;
+        break;
+      }
+      m->ipc_opened.push_back(ptr);
+      h.box[r] = static_cast<Mailbox *>(ptr);
+    }
+    int seg = 0;
+    for (int i = 0; i < m->num_neighbors && all_ok; ++i) {
+      const int q = m->neighbors[i];
+      const PeerCard &c = cards[q];
+      int slot = -1;
+      long long off = c.n;
+      for (int t = 0; t < c.nnb; ++t) {
+        if (c.neighbors[t] == me) {
+          slot = t;
+          break;
+        }
+        off += c.recv_length[t];
+      }
+      if (slot < 0 || c.recv_length[slot] != m->send_length[i])
+        return fail(HPCCG_ERR_STATE, "halo plans of ranks %d and %d do not match", me, q);
+      if (!p_base[q]) {
+        if (cudaIpcOpenMemHandle(&p_base[q], c.p, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          all_ok = false;
+          break;
+        }
+        m->ipc_opened.push_back(p_base[q]);
+      }
+      h.nb_dst[i] = static_cast<double *>(p_base[q]) + off;
+      h.nb_flag[i] = &h.box[q]->halo_seq[slot];
+      h.seg_start[i] = seg;
+      seg += m->send_length[i];
+    }
+    for (int i = m->num_neighbors; i <= kMaxPeerNb; ++i) h.seg_start[i] = seg;
+  }
+  // every rank must take the same decision: one more round
+  int mine_ok = all_ok ? 1 : 0;
+  std::vector<int> oks(R, 0);
+  HPCCG_TRY(nccl_allgather_host(&mine_ok, sizeof(int), oks.data()));
+  for (int v : oks) all_ok = all_ok && v;
+  if (!all_ok) {
+    peer_link_destroy(m);
+    return 0;
+  }
+  HPCCG_CUDA(cudaMalloc(&m->peer_link, sizeof(PeerLink)));
+  HPCCG_CUDA(cudaMemcpy(m->peer_link, &h, sizeof h, cudaMemcpyHostToDevice));
   return 0;
 }
 

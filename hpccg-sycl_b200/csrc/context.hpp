@@ -34,4 +34,16 @@ int nccl_allgather_double(double *buf, cudaStream_t stream);
 int nccl_halo_exchange(const double *send_buffer, const int *send_length, double *recv_base, const int *recv_length,
                        const int *neighbors, int num_neighbors, cudaStream_t stream);
 
+// allgather of `nbytes` per rank through the NCCL communicator (host buffers in, host buffers out)
+int nccl_allgather_host(const void *send, long long nbytes, void *recv);
+
+}  // namespace hpccg
+
+struct hpccg_dev_matrix;
+namespace hpccg {
+// Builds m->peer_link for the calling rank (collective over the NCCL communicator): exchanges IPC handles of every
+// rank's mailbox and p vector, maps the peers' memory and resolves where each send segment lands in its neighbour's p.
+// Leaves m->peer_link == nullptr (NCCL path) when peer memory cannot be used; returns non-zero only on hard errors.
+int peer_link_create(hpccg_dev_matrix *m);
+void peer_link_destroy(hpccg_dev_matrix *m);
 }  // namespace hpccg

@@ -242,7 +242,7 @@ static SpmvPlan plan_tma(int row_begin, int row_end) {
 
 template <int SLOTS, int SPS, int NSTAGES, bool DOT>
 static int launch_tma_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
-                        int total_partials, const FinishParams &fp, cudaStream_t s) {
+                        int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo) {
   if (pl.grid == 0) return 0;
   using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
   if (tma_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>() < 1)
@@ -251,7 +251,7 @@ static int launch_tma_t(const hpccg_dev_matrix *m, const double *x, double *y, c
   const int sb = pl.row_begin / rows;
   spmv_sell_tma_kernel<SLOTS, SPS, NSTAGES, DOT><<<pl.grid, rows, Cfg::kSmemBytes, s>>>(
       m->vals, m->cols, x, y, pl.row_begin, pl.row_end, sb, sb + pl.tiles, m->partials, partial_offset, total_partials,
-      &m->state->counter, fp);
+      &m->state->counter, fp, halo);
   count_launch();
   HPCCG_LAUNCH_CHECK();
   return 0;
@@ -288,8 +288,9 @@ static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end)
 
 template <bool DOT>
 static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
-                       int total_partials, const FinishParams &fp, cudaStream_t s) {
-  if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s);
+                       int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
+  if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
+  if (halo.link) return fail(HPCCG_ERR_STATE, "peer-memory halo wait needs the TMA SpMV path");
   return launch_spmv_reg<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
 }
 
@@ -297,14 +298,14 @@ static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15)
 
 // Whole-matrix SpMV (+ optional fused x.y) in one launch.
 static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool dot, const FinishParams &fp,
-                     cudaStream_t s) {
+                     cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
   if (!aligned16(x) || !aligned16(y)) return fail(HPCCG_ERR_ARG, "SpMV vectors must be 16-byte aligned");
   if (dot) {
     SpmvPlan pl = plan_spmv<true>(m, 0, m->n);
-    return launch_spmv<true>(m, x, y, pl, 0, pl.grid, fp, s);
+    return launch_spmv<true>(m, x, y, pl, 0, pl.grid, fp, s, halo);
   }
   SpmvPlan pl = plan_spmv<false>(m, 0, m->n);
-  return launch_spmv<false>(m, x, y, pl, 0, 0, fp, s);
+  return launch_spmv<false>(m, x, y, pl, 0, 0, fp, s, halo);
 }
 
 static FinishParams fin_store(double *out) {
@@ -640,6 +641,7 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->hist);
   cudaFree(m->scratch_x);
   cudaFree(m->scratch_y);
+  peer_link_destroy(m);
   if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
   if (m->ev_p_ready) cudaEventDestroy(m->ev_p_ready);
   if (m->ev_halo_done) cudaEventDestroy(m->ev_halo_done);
@@ -896,7 +898,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   const int L = (int)rk.size();
   const bool multi = R > 1;
   const bool unfused = (flags & HPCCG_SOLVE_UNFUSED) != 0;
-  const bool overlap = nccl && !(flags & HPCCG_SOLVE_NO_OVERLAP) && !unfused;
+  bool overlap = nccl && !(flags & HPCCG_SOLVE_NO_OVERLAP) && !unfused;
   if (max_iter < 1) max_iter = 1;
   for (auto &q : rk) {
     if (!q.m || !q.b || !q.x) return fail(HPCCG_ERR_ARG, "cg_solve: null argument");
@@ -907,6 +909,15 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   }
   // all local ranks share rank 0's gather array in the in-process world
   double *gathered = rk[0].m->gathered;
+  // Multi-process runs: halos and scalar sums go through peer memory inside the kernels (PeerLink) when every rank
+  // could map its peers and the matrix is served by the TMA SpMV; otherwise NCCL send/recv + gathers between kernels.
+  PeerLink *link = nullptr;
+  if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY) && use_tma_path(rk[0].m->slots)) {
+    HPCCG_TRY(peer_link_create(rk[0].m));
+    link = rk[0].m->peer_link;
+  }
+  const bool p2p = link != nullptr;
+  if (p2p) overlap = false;  // the exchange is hidden inside the single SpMV launch instead
   static thread_local EventTimers timers;
   timers.reset();
   timers.on = (flags & HPCCG_SOLVE_TIMERS) != 0 && times != nullptr;
@@ -925,6 +936,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 
   // -- reduction tail: local sums -> (gather) -> scalar finish on every local rank
   auto finish_multi = [&](int mode, int k, int last, bool check) -> int {
+    if (p2p) return 0;  // already summed over the ranks inside the reducing kernel
     timers.tick(T_ALLRED);
     if (nccl) HPCCG_TRY(nccl_allgather_double(gathered, s));
     for (int q = 0; q < L; ++q) {
@@ -937,6 +949,11 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   };
   auto fp_for = [&](int mode, int q, int k, int last, bool check) {
     if (!multi) return make_fp(mode, rk[q].m, k, last, tol, check);
+    if (p2p) {
+      FinishParams fp = make_fp(mode, rk[q].m, k, last, tol, check);
+      fp.peer = link;
+      return fp;
+    }
     FinishParams fp = make_fp(FIN_STORE, rk[q].m, k, last, tol, check);
     fp.out = gathered + rk[q].grank;
     return fp;
@@ -944,15 +961,29 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   auto do_exchange = [&](bool check) -> int {
     if (!multi) return 0;
     timers.tick(T_EXCH);
-    HPCCG_TRY(exchange_halo(rk, R, nccl, pv.data(), check ? chk.data() : nullptr, s));
+    if (p2p) {
+      hpccg_dev_matrix *m = rk[0].m;
+      if (m->total_to_be_sent > 0) {
+        // one element per thread: the remote stores are posted writes, so the kernel's length is one gather + one
+        // NVLink round trip for the system-scope fence, not a per-thread chain of dependent iterations
+        const int grid = std::max(1, std::min(2048, (m->total_to_be_sent + kThreads - 1) / kThreads));
+        halo_put_kernel<<<grid, kThreads, 0, s>>>(m->total_to_be_sent, m->d_elements_to_send, m->p, link, check ? m->state : nullptr);
+        count_launch();
+        HPCCG_LAUNCH_CHECK();
+      }
+    } else {
+      HPCCG_TRY(exchange_halo(rk, R, nccl, pv.data(), check ? chk.data() : nullptr, s));
+    }
     timers.tock();
     return 0;
   };
+  SpmvHalo halo{};
+  if (p2p) halo = SpmvHalo{link, rk[0].m->n, rk[0].m->interior_begin, rk[0].m->interior_end};
   auto spmv_dot_all = [&](int mode, int k, bool check, bool dot) -> int {
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
       FinishParams fp = dot ? fp_for(mode, q, k, 0, check) : make_fp(FIN_STORE, m, k, 0, tol, check);
-      HPCCG_TRY(spmv_full(m, m->p, m->Ap, dot, fp, s));
+      HPCCG_TRY(spmv_full(m, m->p, m->Ap, dot, fp, s, halo));
     }
     return 0;
   };
@@ -964,6 +995,8 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     HPCCG_CUDA(cudaMemsetAsync(m->hist, 0xFF, sizeof(double) * (max_iter + 1), s));  // NaN = "no iteration ran"
   }
   HPCCG_LAUNCH_CHECK();
+  // one stream-ordered rendezvous per solve: every rank's workspace and peer mappings exist before the first remote store
+  if (p2p) HPCCG_TRY(nccl_allgather_double(gathered, s));
 
   // ---- set-up: p = x ; Ap = A p ; r = b - Ap ; rtrans = r.r (HPCCG.cpp:347-354) ----
   timers.tick(T_WAXPBY);
@@ -1110,6 +1143,12 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   HPCCG_CUDA(cudaMemcpyAsync(&hs, rk[0].m->state, sizeof(CgState), cudaMemcpyDeviceToHost, s));
   if (hist_host) HPCCG_CUDA(cudaMemcpyAsync(hist_host, rk[0].m->hist, sizeof(double) * max_iter, cudaMemcpyDeviceToHost, s));
   HPCCG_CUDA(cudaStreamSynchronize(s));
+  if (p2p) {
+    int perr = 0;
+    HPCCG_CUDA(cudaMemcpy(&perr, &link->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return fail(HPCCG_ERR_COMM, "peer-memory wait timed out (%s): a rank of the job did not arrive",
+                          perr == 2 ? "halo" : "scalar reduction");
+  }
   if (niters_out) *niters_out = hs.niters;
   if (normr_out) *normr_out = hs.normr;
   float ms = 0.f;

@@ -46,6 +46,13 @@ struct hpccg_dev_matrix {
   long long scratch_cap = 0;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_p_ready = nullptr, ev_halo_done = nullptr;
+
+  // peer-memory link (multi-process runs on one NVSwitch domain): mailbox in this rank's HBM, IPC-mapped views of
+  // the peers' mailboxes and of the neighbours' p vectors; peer_link == nullptr: NCCL send/recv + gathers are used
+  hpccg::Mailbox *mailbox = nullptr;
+  hpccg::PeerLink *peer_link = nullptr;   // device copy handed to the kernels
+  std::vector<void *> ipc_opened;         // base pointers returned by cudaIpcOpenMemHandle
+  int peer_tried = 0;
 };
 
 namespace hpccg {

@@ -39,6 +39,7 @@ struct FinishParams {
   CgState *st;
   double *out;      // FIN_STORE target
   double *hist;     // residual history (device), may be null
+  PeerLink *peer;   // non-null: sum the block total over all ranks through peer mailboxes before the finish action
 };
 
 __device__ __forceinline__ void cg_finish(const FinishParams &fp, double sum) {
@@ -102,6 +103,71 @@ __device__ __forceinline__ int ld_stream_s32(const int *p) {
   return v;
 }
 
+// ---- peer-memory primitives (system-scope release / acquire over NVLink) ----------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kPeerTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;  // a dead peer must not hang the GPU
+
+// Spins until *flag >= target.  Returns false on time-out (the caller records the error and carries on with NaN).
+__device__ __forceinline__ bool peer_wait_ge(const unsigned long long *flag, unsigned long long target) {
+  if (ld_acquire_sys(flag) >= target) return true;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < target) {
+    __nanosleep(64);
+    if (global_ns() - t0 > kPeerTimeoutNs) return false;
+  }
+  return true;
+}
+
+// All-reduce (sum in RANK ORDER, so every rank gets the same bits) of one double per rank, executed by the block that
+// finished the local reduction: thread r stores this rank's value + stamp into rank r's mailbox over NVLink and then
+// waits for rank r's value in the local mailbox.  Called by every thread of the block; result valid in thread 0.
+__device__ __forceinline__ double peer_allreduce(PeerLink *pl, double local, double *smem_vals /* >= kMaxRanks */) {
+  __shared__ unsigned long long s_seq;
+  __shared__ double s_local;
+  if (threadIdx.x == 0) {
+    s_seq = ++pl->reduce_seq;
+    s_local = local;
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < pl->size) {
+    const unsigned long long seq = s_seq;
+    const int slot = (int)(seq % kMailSlots);
+    Mailbox *dst = pl->box[t];
+    *reinterpret_cast<volatile double *>(&dst->value[slot][pl->rank]) = s_local;
+    __threadfence_system();
+    st_release_sys(&dst->seq[slot][pl->rank], seq);
+    Mailbox *own = pl->box[pl->rank];
+    double v;
+    if (peer_wait_ge(&own->seq[slot][t], seq)) {
+      v = *reinterpret_cast<volatile double *>(&own->value[slot][t]);
+    } else {
+      pl->error = 1;
+      v = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    smem_vals[t] = v;
+  }
+  __syncthreads();
+  double g = 0.0;
+  if (t == 0) {
+    g = smem_vals[0];
+    for (int r = 1; r < pl->size; ++r) g = __dadd_rn(g, smem_vals[r]);
+  }
+  return g;
+}
+
 // ---- deterministic block reduction + last-block finish ---------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -148,11 +214,16 @@ __device__ __forceinline__ void publish_and_finish_n(double block_total, double 
   acc = warp_sum(acc);
   if (lane == 0) smem[warp] = acc;
   __syncthreads();
+  double r = 0.0;
   if (warp == 0) {
-    double r = (lane < NT / 32) ? smem[lane] : 0.0;
+    r = (lane < NT / 32) ? smem[lane] : 0.0;
     r = warp_sum(r);
-    if (lane == 0) cg_finish(fp, r);
   }
+  if (fp.peer) {  // multi-GPU: the global sum, over peer memory, inside this kernel
+    __shared__ double s_ranks[kMaxRanks];
+    r = peer_allreduce(fp.peer, r, s_ranks);
+  }
+  if (threadIdx.x == 0) cg_finish(fp, r);
 }
 
 __device__ __forceinline__ void publish_and_finish(double block_total, double *partials, int partial_index,
@@ -261,6 +332,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
       : "memory");
 }
 
+// Multi-GPU: rows [0,interior_begin) and [interior_end,n) reference halo columns (>= n) that the neighbours deliver
+// over NVLink WHILE this kernel runs.  The CTAs walk the stages in a rotated order -- interior first, halo-touching
+// stages last -- and a CTA waits for the neighbours' stamps (PeerLink mailbox) only when it reaches such a stage, so
+// the exchange is hidden behind the interior rows inside ONE launch.  link == nullptr: single GPU, natural order.
+struct SpmvHalo {
+  PeerLink *link;
+  int n;               // local_nrow: columns >= n are halo entries (read with ld.global.cg, never through L1)
+  int interior_begin;  // first row that references no halo column
+  int interior_end;
+};
+
 template <int SLOTS, int SPS, int NSTAGES>
 struct SpmvTmaCfg {
   static constexpr int kRows = SPS * kSliceRows;            // rows per stage = threads per CTA
@@ -273,7 +355,7 @@ template <int SLOTS, int SPS, int NSTAGES, bool DOT>
 __global__ void __launch_bounds__(SPS *kSliceRows, 1)
 spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ cols, const double *__restrict__ x,
                      double *__restrict__ y, int row_begin, int row_end, int stage_begin, int stage_end, double *partials,
-                     int partial_offset, int total_partials, unsigned *counter, FinishParams fp) {
+                     int partial_offset, int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo) {
   using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
   constexpr int kRows = Cfg::kRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -284,9 +366,20 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
   if (fp.check_active && fp.st->active == 0) return;
 
   const int tid = threadIdx.x;
-  // stages of this CTA: stage_begin + blockIdx.x + i * gridDim.x
-  const int first = stage_begin + blockIdx.x;
-  const int my_count = first < stage_end ? (stage_end - first + gridDim.x - 1) / gridDim.x : 0;
+  // logical stage g = blockIdx.x + i * gridDim.x of this launch's T stages; physical stage = stage_begin + (g + rot) % T
+  const int T = stage_end - stage_begin;
+  const int my_count = (int)blockIdx.x < T ? (T - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int rot = 0;
+  if (halo.link) {
+    // first stage that lies completely inside the interior; the order becomes interior.., upper halo rows, lower halo rows
+    const int s0 = (halo.interior_begin + kRows - 1) / kRows - stage_begin;
+    rot = (s0 > 0 && s0 < T) ? s0 : 0;
+  }
+  auto phys = [&](int i) {
+    int g = (int)blockIdx.x + i * (int)gridDim.x + rot;
+    if (g >= T) g -= T;
+    return stage_begin + g;
+  };
   unsigned long long policy = 0;
   if (tid == 0) {
     for (int s = 0; s < NSTAGES; ++s) mbar_init(bars + s, 1);
@@ -296,7 +389,7 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
   __syncthreads();
   auto issue = [&](int i) {  // elected thread only
     const int st = i % NSTAGES;
-    const long long stage = first + (long long)i * gridDim.x;
+    const long long stage = phys(i);
     mbar_expect_tx(bars + st, Cfg::kValBytes + Cfg::kColBytes);
     tma_bulk_g2s(sv + (size_t)st * SLOTS * kRows, vals + stage * SLOTS * kRows, Cfg::kValBytes, bars + st, policy);
     tma_bulk_g2s(sc + (size_t)st * SLOTS * kRows, cols + stage * SLOTS * kRows, Cfg::kColBytes, bars + st, policy);
@@ -307,8 +400,21 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
   // thread -> (slice of the stage, row of the slice): shared-memory offset of slot j is soff + j * kSliceRows
   const int soff = (tid / kSliceRows) * SLOTS * kSliceRows + (tid % kSliceRows);
   double dot = 0.0;
+  bool halo_ready = (halo.link == nullptr);
   for (int i = 0; i < my_count; ++i) {
     const int st = i % NSTAGES;
+    const int stage = phys(i);
+    const int row = stage * kRows + tid;
+    const bool touches_halo = halo.link && (stage * kRows < halo.interior_begin || (stage + 1) * kRows > halo.interior_end);
+    if (touches_halo && !halo_ready) {
+      // the neighbours' planes for THIS exchange (stamp = the number the local halo_put_kernel just took) must have landed
+      if (tid < halo.link->nnb) {
+        const Mailbox *own = halo.link->box[halo.link->rank];
+        if (!peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq)) halo.link->error = 2;
+      }
+      __syncthreads();
+      halo_ready = true;
+    }
     mbar_wait(bars + st, (unsigned)(i / NSTAGES) & 1u);
     const double *v = sv + (size_t)st * SLOTS * kRows + soff;
     const int *c = sc + (size_t)st * SLOTS * kRows + soff;
@@ -318,15 +424,23 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
     for (int j = 0; j < SLOTS; ++j) ci[j] = c[j * kSliceRows];
     // all SLOTS gathers are issued back to back and unconditionally (a padding slot reads x[0] and is discarded
     // below), so no predicate is live across the loads and the compiler keeps every gather of the row in flight
+    if (!touches_halo) {
 #pragma unroll
-    for (int j = 0; j < SLOTS; ++j) xv[j] = __ldg(x + max(ci[j], 0));
+      for (int j = 0; j < SLOTS; ++j) xv[j] = __ldg(x + max(ci[j], 0));
+    } else {
+      // halo entries were written by another GPU during this kernel: read them at L2 (ld.global.cg), never through L1
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) {
+        const int cj = max(ci[j], 0);
+        xv[j] = cj >= halo.n ? __ldcg(x + cj) : __ldg(x + cj);
+      }
+    }
     double sum = 0.0;
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
       const double t = __dadd_rn(sum, __dmul_rn(v[j * kSliceRows], xv[j]));
       sum = ci[j] >= 0 ? t : sum;  // padding slots do not exist in the reference's row (HPC_sparsemv.cpp:83-86)
     }
-    const int row = (first + i * (int)gridDim.x) * kRows + tid;
     if (row >= row_begin && row < row_end) {
       y[row] = sum;
       if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + row), sum));
@@ -471,6 +585,36 @@ halo_pack_kernel(int count, const int *__restrict__ elements_to_send, const doub
   if (st_check && st_check->active == 0) return;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads)
     send_buffer[i] = x[elements_to_send[i]];
+}
+
+// ---- exchange_externals.cpp:84-126 over peer memory -------------------------------------------------------------
+// The gather of exchange_externals.cpp:103 and the MPI_Send of :110-112 in one kernel: element i of the send list is
+// stored straight into the neighbour's p vector (its halo tail) through the IPC-mapped pointer, i.e. across NVLink.
+// The block that takes the last ticket publishes the new exchange number in each neighbour's mailbox (release, system
+// scope), which is what the neighbour's SpMV waits for before it touches rows that reference halo columns.
+__global__ void __launch_bounds__(kThreads)
+halo_put_kernel(int count, const int *__restrict__ elements_to_send, const double *__restrict__ x, PeerLink *pl,
+                const CgState *st_check) {
+  if (st_check && st_check->active == 0) return;
+  __shared__ int s_last;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads) {
+    int seg = 0;
+    while (seg + 1 < pl->nnb && i >= pl->seg_start[seg + 1]) ++seg;
+    pl->nb_dst[seg][i - pl->seg_start[seg]] = x[elements_to_send[i]];
+  }
+  __threadfence_system();  // this block's remote stores are visible system-wide before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicInc(&pl->ticket, gridDim.x - 1);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = ++pl->halo_seq;
+    for (int i = 0; i < pl->nnb; ++i) st_release_sys(pl->nb_flag[i], seq);
+  }
 }
 
 // ---- compute_residual.cpp:59-81 (local part): max |v1-v2| ---------------------------------------------
