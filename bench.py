@@ -55,10 +55,11 @@ WORKLOADS = {
 }
 
 
-def bytes_per_row_iter(stencil: int) -> dict:
-    """Algorithmic HBM bytes per local row per CG iteration (SURVEY.md 8d / DESIGN.md): ELL matrix streamed once
-    (8 B value + 4 B column id per slot), p gathered once, Ap written; x,p,r,Ap read + x,r written; r,p read + p written."""
-    spmv = stencil * 12 + 16
+def bytes_per_row_iter(stencil: int, fmt: str = "sell") -> dict:
+    """Algorithmic HBM bytes per local row per CG iteration (SURVEY.md 8d / DESIGN.md): matrix streamed once
+    (8 B value + 4 B column id per slot; 1 B code per slot in the opt-in dictionary format), p gathered once, Ap written;
+    x,p,r,Ap read + x,r written; r,p read + p written."""
+    spmv = stencil * (1 if fmt == "dict" else 12) + 16
     return {"spmv_dot": spmv, "update_xr_dot": 48, "p_update": 24, "iteration": spmv + 72}
 
 
@@ -78,6 +79,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo exchange not overlapped (A/B)")
     ap.add_argument("--unfused", action="store_true", help="literal reference kernel sequence (A/B)")
+    ap.add_argument("--format", default=os.environ.get("HPCCG_BENCH_FORMAT", "sell"), choices=["sell", "dict"],
+                    help="device-mirror format: sell = SELL-128 values + int32 columns (north-star layout, default); "
+                         "dict = lossless one-byte dictionary codes (SURVEY.md 8 f3)")
     ap.add_argument("--cpu-iters", type=int, default=30, help="CG iterations of the CPU reference sample per step")
     return ap.parse_args()
 
@@ -283,6 +287,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
         # host row arrays exist only where the reference itself could hold them (27 n < 2^31 and a sane footprint)
         host_rows = (27 * n < 2 ** 31) and n <= 32 * 1024 * 1024 and size == 1
         H.set_options(stencil, host_rows)
+        H.set_matrix_format(args.format)
         t0 = time.time()
         A = H.generate_matrix(nx, ny, nz)
         if size > 1:
@@ -297,7 +302,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
             flags |= 2
         if args.unfused:
             flags |= 1
-        bpr = bytes_per_row_iter(stencil)
+        bpr = bytes_per_row_iter(stencil, args.format)
 
         def step(acc=None):
             x.zero_()
@@ -334,7 +339,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
         res = {
             "n_local": n, "n_total": n_total, "niters": niters, "normr": last["normr"], "x_max_err": err,
             "ms_per_step": ms_total / steps, "value": flops / (ms_total * 1e-3) / 1e9, "launches": launches, "clocks": clocks,
-            "setup_s": t_setup, "ell_bytes": m.bytes(), "slots": info["slots"],
+            "setup_s": t_setup, "ell_bytes": m.bytes(), "slots": info["slots"], "format": m.format(),
         }
         # per-kernel CUDA-event sums (this rank), on the stream the kernels run on
         it = max(acc["iters"], 1)
@@ -405,7 +410,8 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
     peak, peak_src = measured_peak()
     k = main["kernels"]["spmv_dot"]
     roofline = {"bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": (k["gbs"] or 0) / peak,
-                "traffic": ncu_traffic(w["name"]), "kernel": (f"spmv_sell_tma_kernel<{main['slots']},...,true>" if main["slots"] in (7, 27) and os.environ.get("HPCCG_B200_SPMV") != "reg"
+                "traffic": ncu_traffic(w["name"] + ("" if args.format == "sell" else "-" + args.format)), "kernel": (f"spmv_dict_tma_kernel<{main['slots']},...,true>" if main["format"]["format"] == 1 else
+                           f"spmv_sell_tma_kernel<{main['slots']},...,true>" if main["slots"] in (7, 27) and os.environ.get("HPCCG_B200_SPMV") != "reg"
                            else f"spmv_ell_kernel<{main['slots']},2,true>") + " (fused SpMV + p.Ap)",
                 "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"], "peak_source": peak_src,
                 "loop": {"bytes_per_iteration": main["kernels"]["iteration"]["bytes"],
@@ -440,11 +446,11 @@ def main():
         raise SystemExit("for N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
     w = resolve_workload(args, size)
-    bpr = bytes_per_row_iter(w["stencil"])
+    bpr = bytes_per_row_iter(w["stencil"], args.format)
     config = {"workload": f"{w['name']}: {w['stencil']}-pt stencil, local {w['nx']}x{w['ny']}x{w['nz']} per GPU, "
                           f"global {w['nx']}x{w['ny']}x{w['nz'] * size}, max_iter {args.max_iter} ({args.max_iter - 1} CG iterations per step)",
               "nx": w["nx"], "ny": w["ny"], "nz_local": w["nz"], "stencil": w["stencil"], "max_iter": args.max_iter,
-              "ranks": size, "decomposition": "1-D in z, one rank per GPU (generate_matrix.cpp:225-229)",
+              "ranks": size, "matrix_format": args.format, "decomposition": "1-D in z, one rank per GPU (generate_matrix.cpp:225-229)",
               "bytes_per_row_iteration": bpr["iteration"],
               "l2": "no flush: one iteration streams %.1f GB per GPU, >> 126 MB L2" % (bpr["iteration"] * w["nx"] * w["ny"] * w["nz"] / 1e9)}
     if args.impl == "reference":

@@ -28,7 +28,7 @@ from . import _capi
 from ._capi import HpccgError, check, lib
 
 __all__ = [
-    "HpccgError", "Matrix", "DeviceMatrix", "set_rank", "get_rank", "set_options", "set_print", "generate_matrix",
+    "HpccgError", "Matrix", "DeviceMatrix", "set_matrix_format", "set_rank", "get_rank", "set_options", "set_print", "generate_matrix",
     "make_local_matrix", "HPCCG", "HPC_sparsemv", "ddot", "waxpby", "exchange_externals", "compute_residual",
     "yaml_report", "run_local_world", "launch_count", "dev",
 ]
@@ -119,6 +119,16 @@ class DeviceMatrix:
         check(lib.hpccg_dev_matrix_download(self.handle, vals.ctypes.data, cols.ctypes.data))
         return vals, cols
 
+    def compress(self) -> dict:
+        """Dictionary-coded re-encoding (lossless, bit-identical SpMV); returns format()."""
+        check(lib.hpccg_dev_matrix_compress(self.handle), "hpccg_dev_matrix_compress")
+        return self.format()
+
+    def format(self) -> dict:
+        f, d, r = C.c_int(), C.c_int(), C.c_int()
+        check(lib.hpccg_dev_matrix_format(self.handle, C.byref(f), C.byref(d), C.byref(r)))
+        return {"format": f.value, "dict_entries": d.value, "raw_slices": r.value}
+
     def bytes(self) -> int:
         b = C.c_longlong()
         check(lib.hpccg_dev_matrix_bytes(self.handle, C.byref(b)))
@@ -167,6 +177,12 @@ class Matrix:
             lib.hpccg_api_free_vectors(*self._raw)
             self.handle = None
             self.x = self.b = self.xexact = None
+
+
+def set_matrix_format(fmt) -> None:
+    """Device-mirror format for matrices created from now on: 0 / "sell" (default) or 1 / "dict"."""
+    fmt = {"sell": 0, "dict": 1}.get(fmt, fmt)
+    check(lib.hpccg_api_set_matrix_format(int(fmt)), "hpccg_api_set_matrix_format")
 
 
 def set_print(on: bool) -> None:

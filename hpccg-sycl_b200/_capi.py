@@ -51,6 +51,8 @@ SIGNATURES = {
     "hpccg_dev_matrix_info": (C.c_int, [VP, PI, PI, PI, PLL]),
     "hpccg_dev_matrix_download": (C.c_int, [VP, VP, VP]),
     "hpccg_dev_matrix_bytes": (C.c_int, [VP, PLL]),
+    "hpccg_dev_matrix_compress": (C.c_int, [VP]),
+    "hpccg_dev_matrix_format": (C.c_int, [VP, PI, PI, PI]),
     "hpccg_dev_spmv": (C.c_int, [VP, VP, VP, VP]),
     "hpccg_dev_dot": (C.c_int, [C.c_int, VP, VP, VP, VP]),
     "hpccg_dev_waxpby": (C.c_int, [C.c_int, C.c_double, VP, C.c_double, VP, VP, VP]),
@@ -64,6 +66,7 @@ SIGNATURES = {
     "hpccg_launch_count": (C.c_longlong, []),
     "hpccg_api_set_options": (C.c_int, [C.c_int, C.c_int]),
     "hpccg_api_set_print": (C.c_int, [C.c_int]),
+    "hpccg_api_set_matrix_format": (C.c_int, [C.c_int]),
     "hpccg_api_generate_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, PVP, C.POINTER(PD), C.POINTER(PD), C.POINTER(PD)]),
     "hpccg_api_make_local_matrix": (C.c_int, [VP]),
     "hpccg_api_HPCCG": (C.c_int, [VP, VP, VP, C.c_int, C.c_double, PI, PD, PD]),

@@ -36,6 +36,19 @@ struct CgState {
   unsigned pad;
 };
 
+// ---- dictionary-compressed matrix format (opt-in) -----------------------------------------------
+// Every stored entry of a slice is replaced by a one-byte code into a matrix-wide table of distinct
+// (value, column - row) pairs; slices that use a pair outside the table stay uncompressed ("raw" slices).
+struct DictEntry {
+  double value;
+  int delta;  // column id minus row id
+  int pad;
+};
+constexpr int kDictSize = 256;      // table entries in shared memory (16 B each)
+constexpr int kDictMaxCodes = 254;  // codes 0..253 are table entries
+constexpr int kCodeMissing = 254;   // encoder: pair not in the table -> the slice is kept raw
+constexpr int kCodePadding = 255;   // slot beyond the end of the row
+
 // ---- peer-memory communication (multi-GPU, one process per GPU; NVLink / NVSwitch P2P) ------------------------
 // Replaces MPI_Allreduce (ddot.cpp:79-80) and MPI_Irecv/Send/Wait (exchange_externals.cpp:87-126) INSIDE the kernels:
 // every rank owns a Mailbox in its HBM that its peers write through IPC-mapped pointers.

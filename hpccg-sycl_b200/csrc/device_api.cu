@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -280,8 +281,58 @@ static int tma_variant() {
     }                                                                      \
   } while (0)
 
+// ---- dictionary-compressed format: stages of 2 slices of codes (6.9 KB at 27 slots), 8 stages, several CTAs per SM ----
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static int dict_ctas_per_sm() {
+  static int cached = 0;
+  if (cached) return cached;
+  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
+  auto kern = spmv_dict_tma_kernel<SLOTS, SPS, NSTAGES, DOT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kRows, Cfg::kSmemBytes) != cudaSuccess || per_sm < 1)
+    return -1;
+  cached = per_sm;
+  return cached;
+}
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static SpmvPlan plan_dict(int row_begin, int row_end) {
+  SpmvPlan p{row_begin, row_end, 0, 0};
+  if (row_end <= row_begin) return p;
+  constexpr int rows = SPS * kSliceRows;
+  const int sb = row_begin / rows, se = (row_end + rows - 1) / rows;
+  p.tiles = se - sb;
+  p.grid = std::min(p.tiles, std::max(1, dict_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>()) * device_info().sm_count);
+  return p;
+}
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+static int launch_dict_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                         int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo) {
+  if (pl.grid == 0) return 0;
+  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
+  if (dict_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>() < 1)
+    return fail(HPCCG_ERR_STATE, "dictionary SpMV kernel cannot be resident (%d bytes of shared memory)", Cfg::kSmemBytes);
+  constexpr int rows = Cfg::kRows;
+  const int sb = pl.row_begin / rows;
+  spmv_dict_tma_kernel<SLOTS, SPS, NSTAGES, DOT><<<pl.grid, rows, Cfg::kSmemBytes, s>>>(
+      m->codes, m->dict, m->raw_index, m->raw_vals, m->raw_cols, x, y, m->n, pl.row_begin, pl.row_end, sb, sb + pl.tiles,
+      m->partials, partial_offset, total_partials, &m->state->counter, fp, halo);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+#define HPCCG_DICT_DISPATCH(FN, DOT, ...)                      \
+  do {                                                         \
+    if (m->slots == 7) return FN<7, 2, 8, DOT>(__VA_ARGS__);   \
+    return FN<27, 2, 8, DOT>(__VA_ARGS__);                     \
+  } while (0)
+
 template <bool DOT>
 static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end) {
+  if (m->format == 1) HPCCG_DICT_DISPATCH(plan_dict, DOT, row_begin, row_end);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(plan_tma, DOT, row_begin, row_end);
   return plan_range<2>(row_begin, row_end, spmv_max_grid<DOT>(m->slots));
 }
@@ -289,6 +340,7 @@ static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end)
 template <bool DOT>
 static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
                        int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
+  if (m->format == 1) HPCCG_DICT_DISPATCH(launch_dict_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (halo.link) return fail(HPCCG_ERR_STATE, "peer-memory halo wait needs the TMA SpMV path");
   return launch_spmv_reg<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
@@ -630,6 +682,11 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   if (!m) return 0;
   cudaFree(m->vals);
   cudaFree(m->cols);
+  cudaFree(m->codes);
+  cudaFree(m->dict);
+  cudaFree(m->raw_index);
+  cudaFree(m->raw_vals);
+  cudaFree(m->raw_cols);
   cudaFree(m->d_elements_to_send);
   cudaFree(m->d_send_buffer);
   cudaFree(m->partials);
@@ -660,29 +717,215 @@ int hpccg_dev_matrix_info(const hpccg_dev_matrix *m, int *local_nrow, int *local
 
 int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int *cols_host) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
-  // The device arrays are SELL-C; the caller receives the canonical column-major [slots][padded_rows] view.
+  // The device arrays are SELL-C (or its dictionary-coded form); the caller receives the canonical column-major
+  // [slots][padded_rows] view with the original values and column ids.
   const size_t total = (size_t)m->slots * m->npad;
-  if (vals_host) {
-    std::vector<double> tmp(total);
-    HPCCG_CUDA(cudaMemcpy(tmp.data(), m->vals, sizeof(double) * total, cudaMemcpyDeviceToHost));
-    for (int j = 0; j < m->slots; ++j)
-      for (long long r = 0; r < m->npad; ++r) vals_host[(size_t)j * m->npad + r] = tmp[sell_offset(r, j, m->slots)];
+  std::vector<double> tv(total);
+  std::vector<int> tc(total);
+  if (m->format == 0) {
+    HPCCG_CUDA(cudaMemcpy(tv.data(), m->vals, sizeof(double) * total, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(tc.data(), m->cols, sizeof(int) * total, cudaMemcpyDeviceToHost));
+  } else {
+    const long long nslices = m->npad / kSliceRows;
+    const size_t per_slice = (size_t)m->slots * kSliceRows;
+    std::vector<unsigned char> codes(total);
+    std::vector<DictEntry> dict(kDictSize);
+    std::vector<int> raw_index(nslices);
+    std::vector<double> rv((size_t)m->nraw * per_slice);
+    std::vector<int> rc((size_t)m->nraw * per_slice);
+    HPCCG_CUDA(cudaMemcpy(codes.data(), m->codes, total, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(dict.data(), m->dict, sizeof(DictEntry) * kDictSize, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(raw_index.data(), m->raw_index, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+    if (m->nraw) {
+      HPCCG_CUDA(cudaMemcpy(rv.data(), m->raw_vals, sizeof(double) * rv.size(), cudaMemcpyDeviceToHost));
+      HPCCG_CUDA(cudaMemcpy(rc.data(), m->raw_cols, sizeof(int) * rc.size(), cudaMemcpyDeviceToHost));
+    }
+    for (long long sl = 0; sl < nslices; ++sl)
+      for (size_t k = 0; k < per_slice; ++k) {
+        const size_t o = (size_t)sl * per_slice + k;
+        if (raw_index[sl] >= 0) {
+          tv[o] = rv[(size_t)raw_index[sl] * per_slice + k];
+          tc[o] = rc[(size_t)raw_index[sl] * per_slice + k];
+        } else if (codes[o] == kCodePadding) {
+          tv[o] = 0.0;
+          tc[o] = -1;
+        } else {
+          const long long row = sl * kSliceRows + (long long)(k % kSliceRows);
+          tv[o] = dict[codes[o]].value;
+          tc[o] = (int)(row + dict[codes[o]].delta);
+        }
+      }
   }
-  if (cols_host) {
-    std::vector<int> tmp(total);
-    HPCCG_CUDA(cudaMemcpy(tmp.data(), m->cols, sizeof(int) * total, cudaMemcpyDeviceToHost));
-    for (int j = 0; j < m->slots; ++j)
-      for (long long r = 0; r < m->npad; ++r) cols_host[(size_t)j * m->npad + r] = tmp[sell_offset(r, j, m->slots)];
-  }
+  for (int j = 0; j < m->slots; ++j)
+    for (long long r = 0; r < m->npad; ++r) {
+      if (vals_host) vals_host[(size_t)j * m->npad + r] = tv[sell_offset(r, j, m->slots)];
+      if (cols_host) cols_host[(size_t)j * m->npad + r] = tc[sell_offset(r, j, m->slots)];
+    }
   return 0;
 }
 
 int hpccg_dev_matrix_bytes(const hpccg_dev_matrix *m, long long *bytes) {
   if (!m || !bytes) return fail(HPCCG_ERR_ARG, "null argument");
-  *bytes = (long long)m->slots * m->npad * 12;
+  if (m->format == 0) *bytes = (long long)m->slots * m->npad * 12;
+  else *bytes = (long long)m->slots * m->npad + (long long)m->nraw * m->slots * kSliceRows * 12 + (m->npad / kSliceRows) * 4 +
+                kDictSize * (long long)sizeof(DictEntry);
   return 0;
 }
 
+int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *dict_entries, int *raw_slices) {
+  if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (format) *format = m->format;
+  if (dict_entries) *dict_entries = m->ndict;
+  if (raw_slices) *raw_slices = m->nraw;
+  return 0;
+}
+
+// Lossless re-encoding of the SELL arrays: a matrix-wide table of the distinct (value, column - row)
+// pairs (<= 254, by frequency over sampled slices) and one byte per stored entry.  Slices with a pair outside the table stay
+// uncompressed.  Matrices that do not compress (more than a quarter of the slices raw, or a slot count without a
+// dictionary kernel) are left in format 0; that is not an error.
+int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
+  if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (m->format == 1 || (m->slots != 27 && m->slots != 7)) return 0;
+  const long long nslices = m->npad / kSliceRows;
+  const size_t per_slice = (size_t)m->slots * kSliceRows;
+  struct Pair {
+    long long vbits;
+    int delta;
+    bool operator<(const Pair &o) const { return vbits != o.vbits ? vbits < o.vbits : delta < o.delta; }
+  };
+  std::map<Pair, long long> freq;
+  std::vector<double> hv(per_slice);
+  std::vector<int> hc(per_slice);
+  auto sample_slice = [&](long long sl) -> int {
+    HPCCG_CUDA(cudaMemcpy(hv.data(), m->vals + sl * per_slice, sizeof(double) * per_slice, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(hc.data(), m->cols + sl * per_slice, sizeof(int) * per_slice, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < per_slice; ++k)
+      if (hc[k] >= 0) {
+        Pair pr;
+        std::memcpy(&pr.vbits, &hv[k], 8);
+        pr.delta = (int)(hc[k] - (sl * kSliceRows + (long long)(k % kSliceRows)));
+        freq[pr]++;
+      }
+    return 0;
+  };
+  std::vector<long long> picks;
+  for (long long i = 0; i < std::min<long long>(nslices, 32); ++i) picks.push_back(i);
+  for (long long i = std::max<long long>(0, nslices - 32); i < nslices; ++i) picks.push_back(i);
+  for (int i = 0; i < 256; ++i) picks.push_back(nslices * i / 256);
+  std::sort(picks.begin(), picks.end());
+  picks.erase(std::unique(picks.begin(), picks.end()), picks.end());
+  for (long long sl : picks) HPCCG_TRY(sample_slice(sl));
+
+  unsigned char *codes = nullptr;
+  int *slice_raw = nullptr;
+  DictEntry *dict = nullptr;
+  auto drop = [&] {
+    cudaFree(codes);
+    cudaFree(slice_raw);
+    cudaFree(dict);
+  };
+#define HPCCG_CUDA_DROP(call)                                            \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) {                                             \
+      drop();                                                            \
+      return fail_cuda(e_, #call, __FILE__, __LINE__);                   \
+    }                                                                    \
+  } while (0)
+  HPCCG_CUDA_DROP(cudaMalloc(&codes, (size_t)m->slots * m->npad));
+  HPCCG_CUDA_DROP(cudaMalloc(&slice_raw, sizeof(int) * nslices));
+  HPCCG_CUDA_DROP(cudaMalloc(&dict, sizeof(DictEntry) * kDictSize));
+  std::vector<int> raw_flags(nslices);
+  std::vector<DictEntry> table(kDictSize);
+  int ndict = 0;
+  long long nraw = 0;
+  for (int round = 0; round < 3; ++round) {
+    // table = the most frequent pairs seen so far
+    std::vector<std::pair<long long, Pair>> order;
+    for (auto &kv : freq) order.push_back({kv.second, kv.first});
+    std::sort(order.begin(), order.end(), [](const std::pair<long long, Pair> &a, const std::pair<long long, Pair> &b) {
+      return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    ndict = (int)std::min<size_t>(order.size(), kDictMaxCodes);
+    std::memset(table.data(), 0, sizeof(DictEntry) * kDictSize);
+    for (int e = 0; e < ndict; ++e) {
+      std::memcpy(&table[e].value, &order[e].second.vbits, 8);
+      table[e].delta = order[e].second.delta;
+    }
+    HPCCG_CUDA_DROP(cudaMemcpy(dict, table.data(), sizeof(DictEntry) * kDictSize, cudaMemcpyHostToDevice));
+    HPCCG_CUDA_DROP(cudaMemset(slice_raw, 0, sizeof(int) * nslices));
+    dict_encode_kernel<<<stream_grid(m->npad, 16), kThreads>>>(m->vals, m->cols, m->slots, m->npad, dict, ndict, codes, slice_raw);
+    count_launch();
+    HPCCG_CUDA_DROP(cudaGetLastError());
+    HPCCG_CUDA_DROP(cudaMemcpy(raw_flags.data(), slice_raw, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+    nraw = 0;
+    for (int f : raw_flags) nraw += f ? 1 : 0;
+    if (nraw <= std::max<long long>(16, nslices / 1000) || (int)order.size() >= kDictMaxCodes) break;
+    // widen the sample with some of the slices that did not encode and try again
+    long long taken = 0;
+    for (long long sl = 0; sl < nslices && taken < 256; ++sl)
+      if (raw_flags[sl] && (nraw <= 256 || sl % (nraw / 256 + 1) == 0)) {
+        int rc = sample_slice(sl);
+        if (rc) {
+          drop();
+          return rc;
+        }
+        ++taken;
+      }
+  }
+  if (nraw > nslices / 4) {  // does not compress: stay in format 0
+    drop();
+    return 0;
+  }
+  double *raw_vals = nullptr;
+  int *raw_cols = nullptr;
+  std::vector<int> raw_index(nslices, -1);
+  if (nraw) {
+    cudaError_t e1 = cudaMalloc(&raw_vals, sizeof(double) * (size_t)nraw * per_slice);
+    cudaError_t e2 = cudaMalloc(&raw_cols, sizeof(int) * (size_t)nraw * per_slice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      cudaFree(raw_vals);
+      cudaFree(raw_cols);
+      drop();
+      return fail_cuda(e1 != cudaSuccess ? e1 : e2, "raw slice store", __FILE__, __LINE__);
+    }
+    int k = 0;
+    for (long long sl = 0; sl < nslices; ++sl)
+      if (raw_flags[sl]) {
+        raw_index[sl] = k;
+        cudaMemcpyAsync(raw_vals + (size_t)k * per_slice, m->vals + sl * per_slice, sizeof(double) * per_slice, cudaMemcpyDeviceToDevice, nullptr);
+        cudaMemcpyAsync(raw_cols + (size_t)k * per_slice, m->cols + sl * per_slice, sizeof(int) * per_slice, cudaMemcpyDeviceToDevice, nullptr);
+        ++k;
+      }
+  }
+  cudaError_t e = cudaMemcpy(slice_raw, raw_index.data(), sizeof(int) * nslices, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(raw_vals);
+    cudaFree(raw_cols);
+    drop();
+    return fail_cuda(e, "dictionary encode", __FILE__, __LINE__);
+  }
+#undef HPCCG_CUDA_DROP
+  cudaFree(m->vals);
+  cudaFree(m->cols);
+  m->vals = nullptr;
+  m->cols = nullptr;
+  m->codes = codes;
+  m->dict = dict;
+  m->ndict = ndict;
+  m->raw_index = slice_raw;
+  m->raw_vals = raw_vals;
+  m->raw_cols = raw_cols;
+  m->nraw = (int)nraw;
+  m->format = 1;
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 // ================================================================================================
 // Kernels
 // ================================================================================================
@@ -912,7 +1155,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   // Multi-process runs: halos and scalar sums go through peer memory inside the kernels (PeerLink) when every rank
   // could map its peers and the matrix is served by the TMA SpMV; otherwise NCCL send/recv + gathers between kernels.
   PeerLink *link = nullptr;
-  if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY) && use_tma_path(rk[0].m->slots)) {
+  if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY) && (use_tma_path(rk[0].m->slots) || rk[0].m->format == 1)) {
     HPCCG_TRY(peer_link_create(rk[0].m));
     link = rk[0].m->peer_link;
   }

@@ -24,6 +24,20 @@ struct hpccg_dev_matrix {
   double *vals = nullptr;
   int *cols = nullptr;
 
+  // format 1 (hpccg_dev_matrix_compress): vals/cols are released and replaced by
+  //   codes     : uint8 [slices][slots][128]   one byte per stored entry (same SELL-C addressing as vals/cols)
+  //   dict      : DictEntry[256]               (value, column - row) pairs, matrix-wide
+  //   raw_index : int32 [slices]               -1 = coded slice, else index of the slice in raw_vals / raw_cols
+  //   raw_vals / raw_cols : [nraw][slots][128] the few slices whose pairs are not all in the table
+  int format = 0;
+  unsigned char *codes = nullptr;
+  hpccg::DictEntry *dict = nullptr;
+  int ndict = 0;
+  int *raw_index = nullptr;
+  double *raw_vals = nullptr;
+  int *raw_cols = nullptr;
+  int nraw = 0;
+
   // rows [0,interior_begin) and [interior_end,n) may reference halo columns (>= n); rows in between do not
   int interior_begin = 0, interior_end = 0;
 

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <iostream>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -275,6 +276,14 @@ void install_plan(HPC_Sparse_Matrix *A, const HaloPlan &plan) {
   A->localized = 1;
 }
 
+// The mirror format this thread asked for (hpccg_api_set_matrix_format), else the environment's.
+int wanted_format() {
+  const int f = ctx().matrix_format;
+  if (f >= 0) return f;
+  const char *e = std::getenv("HPCCG_B200_FORMAT");
+  return (e && std::string(e) == "dict") ? 1 : 0;
+}
+
 int get_mirror(HPC_Sparse_Matrix *A, hpccg_dev_matrix **out) {
   if (!A) return fail(HPCCG_ERR_ARG, "null matrix");
   if (!A->device) {
@@ -292,6 +301,13 @@ int get_mirror(HPC_Sparse_Matrix *A, hpccg_dev_matrix **out) {
     if (A->localized) {
       int rc = hpccg_dev_matrix_set_halo(m, A->num_send_neighbors, A->neighbors, A->recv_length, A->send_length,
                                          A->elements_to_send, A->total_to_be_sent);
+      if (rc) {
+        hpccg_dev_matrix_destroy(m);
+        return rc;
+      }
+    }
+    if (wanted_format() == 1) {
+      int rc = hpccg_dev_matrix_compress(m);
       if (rc) {
         hpccg_dev_matrix_destroy(m);
         return rc;
@@ -501,6 +517,7 @@ static int make_local_matrix_impl(HPC_Sparse_Matrix *A) {
                                       upper.empty() ? nullptr : upper.data(), A->local_ncol, &m));
   int rc = hpccg_dev_matrix_set_halo(m, A->num_send_neighbors, A->neighbors, A->recv_length, A->send_length,
                                      A->elements_to_send, A->total_to_be_sent);
+  if (!rc && wanted_format() == 1) rc = hpccg_dev_matrix_compress(m);
   if (rc) {
     hpccg_dev_matrix_destroy(m);
     return rc;
@@ -735,6 +752,12 @@ int hpccg_api_set_options(int stencil, int host_arrays) {
   if (stencil != 27 && stencil != 7) return fail(HPCCG_ERR_ARG, "stencil must be 27 or 7");
   ctx().stencil = stencil;
   ctx().host_arrays = host_arrays ? 1 : 0;
+  return 0;
+}
+
+int hpccg_api_set_matrix_format(int format) {
+  if (format != 0 && format != 1) return fail(HPCCG_ERR_ARG, "matrix format must be 0 (SELL int32) or 1 (dictionary-coded)");
+  ctx().matrix_format = format;
   return 0;
 }
 

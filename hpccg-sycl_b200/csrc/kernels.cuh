@@ -463,6 +463,188 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
   }
 }
 
+// ---- dictionary-compressed SpMV (opt-in format) ------------------------------------------------
+// Same pipeline as spmv_sell_tma_kernel, but a stage is SPS slices of one-byte CODES (SLOTS x 128 bytes per slice,
+// 27x less than values + column ids); the (value, column - row) table sits in shared memory.  The arithmetic is the
+// same un-contracted mul/add in slot order on the same values, so the result is bit-identical to the SELL path.
+// Slices flagged in raw_index (pairs outside the table) are read uncompressed from raw_vals / raw_cols.
+template <int SLOTS, int SPS, int NSTAGES>
+struct SpmvDictCfg {
+  static constexpr int kRows = SPS * kSliceRows;
+  static constexpr int kStageBytes = SLOTS * kRows;  // one byte per entry
+  static constexpr int kSmemBytes = NSTAGES * kStageBytes + kDictSize * (int)sizeof(DictEntry) + NSTAGES * 8 + 64;
+};
+
+template <int SLOTS, int SPS, int NSTAGES, bool DOT>
+__global__ void __launch_bounds__(SPS *kSliceRows, 3)
+spmv_dict_tma_kernel(const unsigned char *__restrict__ codes, const DictEntry *__restrict__ dict,
+                     const int *__restrict__ raw_index, const double *__restrict__ raw_vals,
+                     const int *__restrict__ raw_cols, const double *__restrict__ x, double *__restrict__ y, int n,
+                     int row_begin, int row_end, int stage_begin, int stage_end, double *partials, int partial_offset,
+                     int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo) {
+  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
+  constexpr int kRows = Cfg::kRows;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char *sc = smem_raw;
+  DictEntry *sd = reinterpret_cast<DictEntry *>(smem_raw + NSTAGES * Cfg::kStageBytes);
+  unsigned long long *bars =
+      reinterpret_cast<unsigned long long *>(smem_raw + NSTAGES * Cfg::kStageBytes + kDictSize * sizeof(DictEntry));
+  __shared__ double red[kRows / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+
+  const int tid = threadIdx.x;
+  const int T = stage_end - stage_begin;
+  const int my_count = (int)blockIdx.x < T ? (T - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int rot = 0;
+  if (halo.link) {
+    const int s0 = (halo.interior_begin + kRows - 1) / kRows - stage_begin;
+    rot = (s0 > 0 && s0 < T) ? s0 : 0;
+  }
+  auto phys = [&](int i) {
+    int g = (int)blockIdx.x + i * (int)gridDim.x + rot;
+    if (g >= T) g -= T;
+    return stage_begin + g;
+  };
+  unsigned long long policy = 0;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGES; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  }
+  for (int e = tid; e < kDictSize; e += kRows) sd[e] = dict[e];
+  __syncthreads();
+  auto issue = [&](int i) {
+    const int st = i % NSTAGES;
+    const long long stage = phys(i);
+    mbar_expect_tx(bars + st, Cfg::kStageBytes);
+    tma_bulk_g2s(sc + (size_t)st * Cfg::kStageBytes, codes + stage * Cfg::kStageBytes, Cfg::kStageBytes, bars + st, policy);
+  };
+  if (tid == 0)
+    for (int i = 0; i < NSTAGES && i < my_count; ++i) issue(i);
+
+  const int soff = (tid / kSliceRows) * SLOTS * kSliceRows + (tid % kSliceRows);
+  double dot = 0.0;
+  bool halo_ready = (halo.link == nullptr);
+  for (int i = 0; i < my_count; ++i) {
+    const int st = i % NSTAGES;
+    const int stage = phys(i);
+    const int row = stage * kRows + tid;
+    const bool touches_halo = halo.link && (stage * kRows < halo.interior_begin || (stage + 1) * kRows > halo.interior_end);
+    if (touches_halo && !halo_ready) {
+      if (tid < halo.link->nnb) {
+        const Mailbox *own = halo.link->box[halo.link->rank];
+        if (!peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq)) halo.link->error = 2;
+      }
+      __syncthreads();
+      halo_ready = true;
+    }
+    const int raw = __ldg(raw_index + stage * SPS + tid / kSliceRows);  // uniform over the 4 warps of a slice
+    mbar_wait(bars + st, (unsigned)(i / NSTAGES) & 1u);
+    double sum = 0.0;
+    if (raw < 0) {
+      const unsigned char *c = sc + (size_t)st * Cfg::kStageBytes + soff;
+      const int rowc = min(row, n - 1);  // rows of the padding tail carry only padding codes: keep their dummy gather in range
+      // the row is walked in chunks of CH slots: CH gathers in flight per thread, and few enough registers for three
+      // resident CTAs (24 warps) per SM -- this kernel is bound by instruction issue and L1, not by HBM
+      constexpr int CH = (SLOTS % 9 == 0) ? 9 : SLOTS;
+#pragma unroll
+      for (int j0 = 0; j0 < SLOTS; j0 += CH) {
+        int cb[CH];
+        int cj[CH];
+        double vj[CH], xv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) cb[j] = c[(j0 + j) * kSliceRows];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          // one 128-bit shared-memory load per entry: {value, delta}; the padding code maps to {0.0, 0}
+          const int4 e = *reinterpret_cast<const int4 *>(sd + cb[j]);
+          vj[j] = __hiloint2double(e.y, e.x);
+          cj[j] = rowc + e.z;
+        }
+        if (!touches_halo) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) xv[j] = __ldg(x + cj[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) xv[j] = cj[j] >= halo.n ? __ldcg(x + cj[j]) : __ldg(x + cj[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const double t = __dadd_rn(sum, __dmul_rn(vj[j], xv[j]));
+          sum = cb[j] != kCodePadding ? t : sum;
+        }
+      }
+    } else {
+      // uncompressed slice (a handful per matrix: e.g. the two plane rows whose halo numbering is interleaved)
+      const long long o = ((long long)raw * SLOTS) * kSliceRows + (tid % kSliceRows);
+#pragma unroll 1
+      for (int j = 0; j < SLOTS; ++j) {
+        const int cc = raw_cols[o + j * kSliceRows];
+        if (cc >= 0) {
+          const double xx = (halo.link && cc >= halo.n) ? __ldcg(x + cc) : __ldg(x + cc);
+          sum = __dadd_rn(sum, __dmul_rn(raw_vals[o + j * kSliceRows], xx));
+        }
+      }
+    }
+    if (row >= row_begin && row < row_end) {
+      y[row] = sum;
+      if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + row), sum));
+    }
+    __syncthreads();
+    if (tid == 0 && i + NSTAGES < my_count) issue(i + NSTAGES);
+  }
+  if (DOT) {
+    const int lane = tid & 31, warp = tid >> 5;
+    double w = warp_sum(dot);
+    if (lane == 0) red[warp] = w;
+    __syncthreads();
+    double total = 0.0;
+    if (warp == 0) {
+      total = lane < kRows / 32 ? red[lane] : 0.0;
+      total = warp_sum(total);
+    }
+    publish_and_finish_n<kRows>(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, red);
+  }
+}
+
+// Encoder: one thread per row; looks every stored (value, column - row) pair up in the table and writes its code.
+__global__ void __launch_bounds__(kThreads)
+dict_encode_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, long long npad,
+                   const DictEntry *__restrict__ dict, int ndict, unsigned char *__restrict__ codes,
+                   int *__restrict__ slice_raw) {
+  __shared__ long long s_val[kDictSize];
+  __shared__ int s_delta[kDictSize];
+  for (int e = threadIdx.x; e < ndict; e += kThreads) {
+    s_val[e] = __double_as_longlong(dict[e].value);
+    s_delta[e] = dict[e].delta;
+  }
+  __syncthreads();
+  for (long long row = (long long)blockIdx.x * kThreads + threadIdx.x; row < npad; row += (long long)gridDim.x * kThreads) {
+    int last = 0;  // neighbouring entries of a row usually sit next to each other in the table
+    for (int j = 0; j < slots; ++j) {
+      const long long o = sell_offset(row, j, slots);
+      const int c = cols[o];
+      int code = kCodePadding;
+      if (c >= 0) {
+        const long long vb = __double_as_longlong(vals[o]);
+        const int d = (int)(c - row);
+        code = kCodeMissing;
+        for (int t = 0; t < ndict; ++t) {
+          int e = last + t;
+          if (e >= ndict) e -= ndict;
+          if (s_val[e] == vb && s_delta[e] == d) {
+            code = e;
+            last = e;
+            break;
+          }
+        }
+        if (code == kCodeMissing) slice_raw[row / kSliceRows] = 1;
+      }
+      codes[o] = (unsigned char)code;
+    }
+  }
+}
+
 // ---- ddot.cpp:60-74 ----------------------------------------------------------------------------------
 template <bool SAME>
 __global__ void __launch_bounds__(kThreads)
