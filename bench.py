@@ -57,9 +57,9 @@ WORKLOADS = {
 
 def bytes_per_row_iter(stencil: int, fmt: str = "sell") -> dict:
     """Algorithmic HBM bytes per local row per CG iteration (SURVEY.md 8d / DESIGN.md): matrix streamed once
-    (8 B value + 4 B column id per slot; 1 B code per slot in the opt-in dictionary format), p gathered once, Ap written;
+    (8 B value + 4 B column id per slot; one 2-byte pattern id per row in the opt-in pattern format), p gathered once, Ap written;
     x,p,r,Ap read + x,r written; r,p read + p written."""
-    spmv = stencil * (1 if fmt == "dict" else 12) + 16
+    spmv = (2 if fmt == "pattern" else stencil * 12) + 16
     return {"spmv_dot": spmv, "update_xr_dot": 48, "p_update": 24, "iteration": spmv + 72}
 
 
@@ -79,9 +79,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo exchange not overlapped (A/B)")
     ap.add_argument("--unfused", action="store_true", help="literal reference kernel sequence (A/B)")
-    ap.add_argument("--format", default=os.environ.get("HPCCG_BENCH_FORMAT", "sell"), choices=["sell", "dict"],
+    ap.add_argument("--format", default=os.environ.get("HPCCG_BENCH_FORMAT", "sell"), choices=["sell", "pattern"],
                     help="device-mirror format: sell = SELL-128 values + int32 columns (north-star layout, default); "
-                         "dict = lossless one-byte dictionary codes (SURVEY.md 8 f3)")
+                         "pattern = lossless 16-bit row-pattern ids (SURVEY.md 8 f3)")
     ap.add_argument("--cpu-iters", type=int, default=30, help="CG iterations of the CPU reference sample per step")
     return ap.parse_args()
 
@@ -410,7 +410,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
     peak, peak_src = measured_peak()
     k = main["kernels"]["spmv_dot"]
     roofline = {"bound": "hbm", "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": (k["gbs"] or 0) / peak,
-                "traffic": ncu_traffic(w["name"] + ("" if args.format == "sell" else "-" + args.format)), "kernel": (f"spmv_dict_tma_kernel<{main['slots']},...,true>" if main["format"]["format"] == 1 else
+                "traffic": ncu_traffic(w["name"] + ("" if args.format == "sell" else "-" + args.format)), "kernel": (f"spmv_pattern_kernel<{main['slots']},true>" if main["format"]["format"] == 1 else
                            f"spmv_sell_tma_kernel<{main['slots']},...,true>" if main["slots"] in (7, 27) and os.environ.get("HPCCG_B200_SPMV") != "reg"
                            else f"spmv_ell_kernel<{main['slots']},2,true>") + " (fused SpMV + p.Ap)",
                 "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"], "peak_source": peak_src,

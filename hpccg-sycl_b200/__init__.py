@@ -120,14 +120,14 @@ class DeviceMatrix:
         return vals, cols
 
     def compress(self) -> dict:
-        """Dictionary-coded re-encoding (lossless, bit-identical SpMV); returns format()."""
+        """Pattern-coded re-encoding (lossless, bit-identical SpMV); returns format()."""
         check(lib.hpccg_dev_matrix_compress(self.handle), "hpccg_dev_matrix_compress")
         return self.format()
 
     def format(self) -> dict:
-        f, d, r = C.c_int(), C.c_int(), C.c_int()
-        check(lib.hpccg_dev_matrix_format(self.handle, C.byref(f), C.byref(d), C.byref(r)))
-        return {"format": f.value, "dict_entries": d.value, "raw_slices": r.value}
+        f, p = C.c_int(), C.c_int()
+        check(lib.hpccg_dev_matrix_format(self.handle, C.byref(f), C.byref(p)))
+        return {"format": f.value, "patterns": p.value}
 
     def bytes(self) -> int:
         b = C.c_longlong()
@@ -180,8 +180,8 @@ class Matrix:
 
 
 def set_matrix_format(fmt) -> None:
-    """Device-mirror format for matrices created from now on: 0 / "sell" (default) or 1 / "dict"."""
-    fmt = {"sell": 0, "dict": 1}.get(fmt, fmt)
+    """Device-mirror format for matrices created from now on: 0 / "sell" (default) or 1 / "pattern"."""
+    fmt = {"sell": 0, "pattern": 1}.get(fmt, fmt)
     check(lib.hpccg_api_set_matrix_format(int(fmt)), "hpccg_api_set_matrix_format")
 
 

@@ -36,18 +36,21 @@ struct CgState {
   unsigned pad;
 };
 
-// ---- dictionary-compressed matrix format (opt-in) -----------------------------------------------
-// Every stored entry of a slice is replaced by a one-byte code into a matrix-wide table of distinct
-// (value, column - row) pairs; slices that use a pair outside the table stay uncompressed ("raw" slices).
-struct DictEntry {
-  double value;
-  int delta;  // column id minus row id
+// ---- pattern-coded matrix format (opt-in) ----------------------------------------------------------
+// A row's PATTERN is its sequence of stored (value, column - row) pairs.  Stencil-like matrices have very few distinct
+// patterns (27-pt: one per boundary type, plus the halo variants), so the mirror keeps ONE 16-bit pattern id per row and
+// a small pattern table instead of 12 bytes per stored entry.  Lossless: same values, same columns, same order.
+constexpr int kMaxPatterns = 65535;   // ids are uint16; 0xFFFF marks the rows of the padding tail
+constexpr int kPatternSlots = 32;     // capacity of the constant-bank copy of pattern 0
+// Pattern 0 (the most frequent one) as the SpMV kernel receives it: a __grid_constant__ kernel parameter.  In the
+// warp-uniform fast path its values and deltas are constant-bank OPERANDS of the multiply / address instructions,
+// i.e. the matrix costs no load instruction at all there.
+struct Pattern0 {
+  double value[kPatternSlots];
+  int delta[kPatternSlots];
+  int len;
   int pad;
 };
-constexpr int kDictSize = 256;      // table entries in shared memory (16 B each)
-constexpr int kDictMaxCodes = 254;  // codes 0..253 are table entries
-constexpr int kCodeMissing = 254;   // encoder: pair not in the table -> the slice is kept raw
-constexpr int kCodePadding = 255;   // slot beyond the end of the row
 
 // ---- peer-memory communication (multi-GPU, one process per GPU; NVLink / NVSwitch P2P) ------------------------
 // Replaces MPI_Allreduce (ddot.cpp:79-80) and MPI_Irecv/Send/Wait (exchange_externals.cpp:87-126) INSIDE the kernels:

@@ -18,7 +18,7 @@ struct RankContext {
   int stencil = 27;     // generate_matrix.cpp:219
   int host_arrays = 1;  // 0: device-only generation
   int print_residuals = 1;  // HPCCG() prints the reference's residual lines on rank 0
-  int matrix_format = -1;   // -1: environment (HPCCG_B200_FORMAT=dict -> 1) else 0; 0: SELL int32; 1: dictionary-coded
+  int matrix_format = -1;   // -1: environment (HPCCG_B200_FORMAT=pattern -> 1) else 0; 0: SELL int32; 1: pattern-coded
 };
 
 RankContext &ctx();  // thread-local

@@ -281,58 +281,50 @@ static int tma_variant() {
     }                                                                      \
   } while (0)
 
-// ---- dictionary-compressed format: stages of 2 slices of codes (6.9 KB at 27 slots), 8 stages, several CTAs per SM ----
-template <int SLOTS, int SPS, int NSTAGES, bool DOT>
-static int dict_ctas_per_sm() {
+// ---- pattern-coded format: tiles of kThreads rows, persistent CTAs ------------------------------------------------
+template <int SLOTS, bool DOT>
+static int pattern_ctas_per_sm() {
   static int cached = 0;
   if (cached) return cached;
-  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
-  auto kern = spmv_dict_tma_kernel<SLOTS, SPS, NSTAGES, DOT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return -1;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kRows, Cfg::kSmemBytes) != cudaSuccess || per_sm < 1)
-    return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_kernel<SLOTS, DOT>, kThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
   cached = per_sm;
   return cached;
 }
 
-template <int SLOTS, int SPS, int NSTAGES, bool DOT>
-static SpmvPlan plan_dict(int row_begin, int row_end) {
+template <int SLOTS, bool DOT>
+static SpmvPlan plan_pattern(int row_begin, int row_end) {
   SpmvPlan p{row_begin, row_end, 0, 0};
   if (row_end <= row_begin) return p;
-  constexpr int rows = SPS * kSliceRows;
-  const int sb = row_begin / rows, se = (row_end + rows - 1) / rows;
-  p.tiles = se - sb;
-  p.grid = std::min(p.tiles, std::max(1, dict_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>()) * device_info().sm_count);
+  const int tb = row_begin / kThreads, te = (row_end + kThreads - 1) / kThreads;
+  p.tiles = te - tb;
+  p.grid = std::min(p.tiles, std::min(pattern_ctas_per_sm<SLOTS, DOT>() * device_info().sm_count, kMaxPartials / 4));
   return p;
 }
 
-template <int SLOTS, int SPS, int NSTAGES, bool DOT>
-static int launch_dict_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
-                         int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo) {
+template <int SLOTS, bool DOT>
+static int launch_pattern_t(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                            int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo) {
   if (pl.grid == 0) return 0;
-  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
-  if (dict_ctas_per_sm<SLOTS, SPS, NSTAGES, DOT>() < 1)
-    return fail(HPCCG_ERR_STATE, "dictionary SpMV kernel cannot be resident (%d bytes of shared memory)", Cfg::kSmemBytes);
-  constexpr int rows = Cfg::kRows;
-  const int sb = pl.row_begin / rows;
-  spmv_dict_tma_kernel<SLOTS, SPS, NSTAGES, DOT><<<pl.grid, rows, Cfg::kSmemBytes, s>>>(
-      m->codes, m->dict, m->raw_index, m->raw_vals, m->raw_cols, x, y, m->n, pl.row_begin, pl.row_end, sb, sb + pl.tiles,
-      m->partials, partial_offset, total_partials, &m->state->counter, fp, halo);
+  const int tb = pl.row_begin / kThreads;
+  spmv_pattern_kernel<SLOTS, DOT><<<pl.grid, kThreads, 0, s>>>(m->pat_id, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, x, y,
+                                                               m->n, pl.row_begin, pl.row_end, tb, tb + pl.tiles, m->partials,
+                                                               partial_offset, total_partials, &m->state->counter, fp, halo);
   count_launch();
   HPCCG_LAUNCH_CHECK();
   return 0;
 }
 
-#define HPCCG_DICT_DISPATCH(FN, DOT, ...)                      \
-  do {                                                         \
-    if (m->slots == 7) return FN<7, 2, 8, DOT>(__VA_ARGS__);   \
-    return FN<27, 2, 8, DOT>(__VA_ARGS__);                     \
+#define HPCCG_PATTERN_DISPATCH(FN, DOT, ...)             \
+  do {                                                   \
+    if (m->slots == 7) return FN<7, DOT>(__VA_ARGS__);   \
+    return FN<27, DOT>(__VA_ARGS__);                     \
   } while (0)
 
 template <bool DOT>
 static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end) {
-  if (m->format == 1) HPCCG_DICT_DISPATCH(plan_dict, DOT, row_begin, row_end);
+  if (m->format == 1) HPCCG_PATTERN_DISPATCH(plan_pattern, DOT, row_begin, row_end);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(plan_tma, DOT, row_begin, row_end);
   return plan_range<2>(row_begin, row_end, spmv_max_grid<DOT>(m->slots));
 }
@@ -340,7 +332,7 @@ static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end)
 template <bool DOT>
 static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
                        int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
-  if (m->format == 1) HPCCG_DICT_DISPATCH(launch_dict_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
+  if (m->format == 1) HPCCG_PATTERN_DISPATCH(launch_pattern_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (halo.link) return fail(HPCCG_ERR_STATE, "peer-memory halo wait needs the TMA SpMV path");
   return launch_spmv_reg<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
@@ -682,11 +674,10 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   if (!m) return 0;
   cudaFree(m->vals);
   cudaFree(m->cols);
-  cudaFree(m->codes);
-  cudaFree(m->dict);
-  cudaFree(m->raw_index);
-  cudaFree(m->raw_vals);
-  cudaFree(m->raw_cols);
+  cudaFree(m->pat_id);
+  cudaFree(m->pat_val);
+  cudaFree(m->pat_delta);
+  cudaFree(m->pat_len);
   cudaFree(m->d_elements_to_send);
   cudaFree(m->d_send_buffer);
   cudaFree(m->partials);
@@ -717,113 +708,75 @@ int hpccg_dev_matrix_info(const hpccg_dev_matrix *m, int *local_nrow, int *local
 
 int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int *cols_host) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
-  // The device arrays are SELL-C (or its dictionary-coded form); the caller receives the canonical column-major
+  // The device arrays are SELL-C (or pattern-coded); the caller receives the canonical column-major
   // [slots][padded_rows] view with the original values and column ids.
   const size_t total = (size_t)m->slots * m->npad;
-  std::vector<double> tv(total);
-  std::vector<int> tc(total);
   if (m->format == 0) {
-    HPCCG_CUDA(cudaMemcpy(tv.data(), m->vals, sizeof(double) * total, cudaMemcpyDeviceToHost));
-    HPCCG_CUDA(cudaMemcpy(tc.data(), m->cols, sizeof(int) * total, cudaMemcpyDeviceToHost));
-  } else {
-    const long long nslices = m->npad / kSliceRows;
-    const size_t per_slice = (size_t)m->slots * kSliceRows;
-    std::vector<unsigned char> codes(total);
-    std::vector<DictEntry> dict(kDictSize);
-    std::vector<int> raw_index(nslices);
-    std::vector<double> rv((size_t)m->nraw * per_slice);
-    std::vector<int> rc((size_t)m->nraw * per_slice);
-    HPCCG_CUDA(cudaMemcpy(codes.data(), m->codes, total, cudaMemcpyDeviceToHost));
-    HPCCG_CUDA(cudaMemcpy(dict.data(), m->dict, sizeof(DictEntry) * kDictSize, cudaMemcpyDeviceToHost));
-    HPCCG_CUDA(cudaMemcpy(raw_index.data(), m->raw_index, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
-    if (m->nraw) {
-      HPCCG_CUDA(cudaMemcpy(rv.data(), m->raw_vals, sizeof(double) * rv.size(), cudaMemcpyDeviceToHost));
-      HPCCG_CUDA(cudaMemcpy(rc.data(), m->raw_cols, sizeof(int) * rc.size(), cudaMemcpyDeviceToHost));
-    }
-    for (long long sl = 0; sl < nslices; ++sl)
-      for (size_t k = 0; k < per_slice; ++k) {
-        const size_t o = (size_t)sl * per_slice + k;
-        if (raw_index[sl] >= 0) {
-          tv[o] = rv[(size_t)raw_index[sl] * per_slice + k];
-          tc[o] = rc[(size_t)raw_index[sl] * per_slice + k];
-        } else if (codes[o] == kCodePadding) {
-          tv[o] = 0.0;
-          tc[o] = -1;
-        } else {
-          const long long row = sl * kSliceRows + (long long)(k % kSliceRows);
-          tv[o] = dict[codes[o]].value;
-          tc[o] = (int)(row + dict[codes[o]].delta);
-        }
+    std::vector<double> tv(vals_host ? total : 0);
+    std::vector<int> tc(cols_host ? total : 0);
+    if (vals_host) HPCCG_CUDA(cudaMemcpy(tv.data(), m->vals, sizeof(double) * total, cudaMemcpyDeviceToHost));
+    if (cols_host) HPCCG_CUDA(cudaMemcpy(tc.data(), m->cols, sizeof(int) * total, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < m->slots; ++j)
+      for (long long r = 0; r < m->npad; ++r) {
+        if (vals_host) vals_host[(size_t)j * m->npad + r] = tv[sell_offset(r, j, m->slots)];
+        if (cols_host) cols_host[(size_t)j * m->npad + r] = tc[sell_offset(r, j, m->slots)];
       }
+    return 0;
   }
-  for (int j = 0; j < m->slots; ++j)
-    for (long long r = 0; r < m->npad; ++r) {
-      if (vals_host) vals_host[(size_t)j * m->npad + r] = tv[sell_offset(r, j, m->slots)];
-      if (cols_host) cols_host[(size_t)j * m->npad + r] = tc[sell_offset(r, j, m->slots)];
+  std::vector<unsigned short> ids(m->npad);
+  std::vector<double> pv((size_t)m->npat * m->slots);
+  std::vector<int> pd((size_t)m->npat * m->slots), plen(m->npat);
+  HPCCG_CUDA(cudaMemcpy(ids.data(), m->pat_id, sizeof(unsigned short) * m->npad, cudaMemcpyDeviceToHost));
+  HPCCG_CUDA(cudaMemcpy(pv.data(), m->pat_val, sizeof(double) * pv.size(), cudaMemcpyDeviceToHost));
+  HPCCG_CUDA(cudaMemcpy(pd.data(), m->pat_delta, sizeof(int) * pd.size(), cudaMemcpyDeviceToHost));
+  HPCCG_CUDA(cudaMemcpy(plen.data(), m->pat_len, sizeof(int) * plen.size(), cudaMemcpyDeviceToHost));
+  for (long long r = 0; r < m->npad; ++r) {
+    const int id = ids[r];
+    const int len = id == 0xFFFF ? 0 : plen[id];
+    for (int j = 0; j < m->slots; ++j) {
+      if (vals_host) vals_host[(size_t)j * m->npad + r] = j < len ? pv[(size_t)id * m->slots + j] : 0.0;
+      if (cols_host) cols_host[(size_t)j * m->npad + r] = j < len ? (int)(r + pd[(size_t)id * m->slots + j]) : -1;
     }
+  }
   return 0;
 }
 
 int hpccg_dev_matrix_bytes(const hpccg_dev_matrix *m, long long *bytes) {
   if (!m || !bytes) return fail(HPCCG_ERR_ARG, "null argument");
   if (m->format == 0) *bytes = (long long)m->slots * m->npad * 12;
-  else *bytes = (long long)m->slots * m->npad + (long long)m->nraw * m->slots * kSliceRows * 12 + (m->npad / kSliceRows) * 4 +
-                kDictSize * (long long)sizeof(DictEntry);
+  else *bytes = 2LL * m->npad + (long long)m->npat * (m->slots * 12 + 4);
   return 0;
 }
 
-int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *dict_entries, int *raw_slices) {
+int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *patterns) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
   if (format) *format = m->format;
-  if (dict_entries) *dict_entries = m->ndict;
-  if (raw_slices) *raw_slices = m->nraw;
+  if (patterns) *patterns = m->npat;
   return 0;
 }
 
-// Lossless re-encoding of the SELL arrays: a matrix-wide table of the distinct (value, column - row)
-// pairs (<= 254, by frequency over sampled slices) and one byte per stored entry.  Slices with a pair outside the table stay
-// uncompressed.  Matrices that do not compress (more than a quarter of the slices raw, or a slot count without a
-// dictionary kernel) are left in format 0; that is not an error.
+// Lossless re-encoding of the SELL arrays: the distinct row patterns -- sequences of (value, column - row)
+// pairs -- are collected in a device hash table, numbered, checked entry by entry against every row, and the mirror
+// keeps one 16-bit id per row.  A matrix with more than 65535 patterns (or a slot count without a pattern kernel) is
+// left in format 0; that is not an error.
 int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
-  if (m->format == 1 || (m->slots != 27 && m->slots != 7)) return 0;
-  const long long nslices = m->npad / kSliceRows;
-  const size_t per_slice = (size_t)m->slots * kSliceRows;
-  struct Pair {
-    long long vbits;
-    int delta;
-    bool operator<(const Pair &o) const { return vbits != o.vbits ? vbits < o.vbits : delta < o.delta; }
-  };
-  std::map<Pair, long long> freq;
-  std::vector<double> hv(per_slice);
-  std::vector<int> hc(per_slice);
-  auto sample_slice = [&](long long sl) -> int {
-    HPCCG_CUDA(cudaMemcpy(hv.data(), m->vals + sl * per_slice, sizeof(double) * per_slice, cudaMemcpyDeviceToHost));
-    HPCCG_CUDA(cudaMemcpy(hc.data(), m->cols + sl * per_slice, sizeof(int) * per_slice, cudaMemcpyDeviceToHost));
-    for (size_t k = 0; k < per_slice; ++k)
-      if (hc[k] >= 0) {
-        Pair pr;
-        std::memcpy(&pr.vbits, &hv[k], 8);
-        pr.delta = (int)(hc[k] - (sl * kSliceRows + (long long)(k % kSliceRows)));
-        freq[pr]++;
-      }
-    return 0;
-  };
-  std::vector<long long> picks;
-  for (long long i = 0; i < std::min<long long>(nslices, 32); ++i) picks.push_back(i);
-  for (long long i = std::max<long long>(0, nslices - 32); i < nslices; ++i) picks.push_back(i);
-  for (int i = 0; i < 256; ++i) picks.push_back(nslices * i / 256);
-  std::sort(picks.begin(), picks.end());
-  picks.erase(std::unique(picks.begin(), picks.end()), picks.end());
-  for (long long sl : picks) HPCCG_TRY(sample_slice(sl));
-
-  unsigned char *codes = nullptr;
-  int *slice_raw = nullptr;
-  DictEntry *dict = nullptr;
+  if (m->format == 1 || (m->slots != 27 && m->slots != 7) || m->slots > kPatternSlots) return 0;
+  const unsigned table_size = 1u << 21, mask = table_size - 1;
+  unsigned long long *keys = nullptr, *freq = nullptr;
+  int *ids = nullptr, *scal = nullptr, *rep = nullptr, *pat_delta = nullptr, *pat_len = nullptr;
+  unsigned short *pat_id = nullptr;
+  double *pat_val = nullptr;
   auto drop = [&] {
-    cudaFree(codes);
-    cudaFree(slice_raw);
-    cudaFree(dict);
+    cudaFree(keys);
+    cudaFree(freq);
+    cudaFree(ids);
+    cudaFree(scal);
+    cudaFree(rep);
+    cudaFree(pat_delta);
+    cudaFree(pat_len);
+    cudaFree(pat_id);
+    cudaFree(pat_val);
   };
 #define HPCCG_CUDA_DROP(call)                                            \
   do {                                                                   \
@@ -833,92 +786,82 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
       return fail_cuda(e_, #call, __FILE__, __LINE__);                   \
     }                                                                    \
   } while (0)
-  HPCCG_CUDA_DROP(cudaMalloc(&codes, (size_t)m->slots * m->npad));
-  HPCCG_CUDA_DROP(cudaMalloc(&slice_raw, sizeof(int) * nslices));
-  HPCCG_CUDA_DROP(cudaMalloc(&dict, sizeof(DictEntry) * kDictSize));
-  std::vector<int> raw_flags(nslices);
-  std::vector<DictEntry> table(kDictSize);
-  int ndict = 0;
-  long long nraw = 0;
-  for (int round = 0; round < 3; ++round) {
-    // table = the most frequent pairs seen so far
-    std::vector<std::pair<long long, Pair>> order;
-    for (auto &kv : freq) order.push_back({kv.second, kv.first});
-    std::sort(order.begin(), order.end(), [](const std::pair<long long, Pair> &a, const std::pair<long long, Pair> &b) {
-      return a.first != b.first ? a.first > b.first : a.second < b.second;
-    });
-    ndict = (int)std::min<size_t>(order.size(), kDictMaxCodes);
-    std::memset(table.data(), 0, sizeof(DictEntry) * kDictSize);
-    for (int e = 0; e < ndict; ++e) {
-      std::memcpy(&table[e].value, &order[e].second.vbits, 8);
-      table[e].delta = order[e].second.delta;
-    }
-    HPCCG_CUDA_DROP(cudaMemcpy(dict, table.data(), sizeof(DictEntry) * kDictSize, cudaMemcpyHostToDevice));
-    HPCCG_CUDA_DROP(cudaMemset(slice_raw, 0, sizeof(int) * nslices));
-    dict_encode_kernel<<<stream_grid(m->npad, 16), kThreads>>>(m->vals, m->cols, m->slots, m->npad, dict, ndict, codes, slice_raw);
-    count_launch();
-    HPCCG_CUDA_DROP(cudaGetLastError());
-    HPCCG_CUDA_DROP(cudaMemcpy(raw_flags.data(), slice_raw, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
-    nraw = 0;
-    for (int f : raw_flags) nraw += f ? 1 : 0;
-    if (nraw <= std::max<long long>(16, nslices / 1000) || (int)order.size() >= kDictMaxCodes) break;
-    // widen the sample with some of the slices that did not encode and try again
-    long long taken = 0;
-    for (long long sl = 0; sl < nslices && taken < 256; ++sl)
-      if (raw_flags[sl] && (nraw <= 256 || sl % (nraw / 256 + 1) == 0)) {
-        int rc = sample_slice(sl);
-        if (rc) {
-          drop();
-          return rc;
-        }
-        ++taken;
-      }
-  }
-  if (nraw > nslices / 4) {  // does not compress: stay in format 0
+  HPCCG_CUDA_DROP(cudaMalloc(&keys, sizeof(unsigned long long) * table_size));
+  HPCCG_CUDA_DROP(cudaMalloc(&ids, sizeof(int) * table_size));
+  HPCCG_CUDA_DROP(cudaMalloc(&scal, sizeof(int) * 4));  // [0] overflow, [1] pattern count, [2] mismatch
+  HPCCG_CUDA_DROP(cudaMemset(keys, 0, sizeof(unsigned long long) * table_size));
+  HPCCG_CUDA_DROP(cudaMemset(scal, 0, sizeof(int) * 4));
+  const int grid = stream_grid(m->npad, 16);
+  pattern_insert_kernel<<<grid, kThreads>>>(m->vals, m->cols, m->slots, m->n, keys, mask, scal);
+  pattern_number_kernel<<<stream_grid(table_size, 16), kThreads>>>(keys, table_size, ids, scal + 1);
+  count_launch(2);
+  int h_scal[4] = {0, 0, 0, 0};
+  HPCCG_CUDA_DROP(cudaMemcpy(h_scal, scal, sizeof h_scal, cudaMemcpyDeviceToHost));
+  const int npat = h_scal[1];
+  if (h_scal[0] || npat > kMaxPatterns || npat < 1) {  // does not compress: stay in format 0
     drop();
     return 0;
   }
-  double *raw_vals = nullptr;
-  int *raw_cols = nullptr;
-  std::vector<int> raw_index(nslices, -1);
-  if (nraw) {
-    cudaError_t e1 = cudaMalloc(&raw_vals, sizeof(double) * (size_t)nraw * per_slice);
-    cudaError_t e2 = cudaMalloc(&raw_cols, sizeof(int) * (size_t)nraw * per_slice);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      cudaFree(raw_vals);
-      cudaFree(raw_cols);
-      drop();
-      return fail_cuda(e1 != cudaSuccess ? e1 : e2, "raw slice store", __FILE__, __LINE__);
+  HPCCG_CUDA_DROP(cudaMalloc(&pat_id, sizeof(unsigned short) * m->npad));
+  HPCCG_CUDA_DROP(cudaMalloc(&rep, sizeof(int) * npat));
+  HPCCG_CUDA_DROP(cudaMalloc(&freq, sizeof(unsigned long long) * npat));
+  HPCCG_CUDA_DROP(cudaMemset(freq, 0, sizeof(unsigned long long) * npat));
+  HPCCG_CUDA_DROP(cudaMalloc(&pat_val, sizeof(double) * (size_t)npat * m->slots));
+  HPCCG_CUDA_DROP(cudaMalloc(&pat_delta, sizeof(int) * (size_t)npat * m->slots));
+  HPCCG_CUDA_DROP(cudaMalloc(&pat_len, sizeof(int) * npat));
+  pattern_assign_kernel<<<grid, kThreads>>>(m->vals, m->cols, m->slots, m->n, m->npad, keys, ids, mask, pat_id, rep, freq);
+  pattern_fill_kernel<<<stream_grid(npat, 16), kThreads>>>(m->vals, m->cols, m->slots, npat, rep, pat_val, pat_delta, pat_len);
+  count_launch(2);
+  // the most frequent pattern becomes id 0 (the constant-bank fast path of the SpMV)
+  std::vector<unsigned long long> h_freq(npat);
+  std::vector<double> h_val((size_t)npat * m->slots);
+  std::vector<int> h_delta((size_t)npat * m->slots), h_len(npat);
+  HPCCG_CUDA_DROP(cudaMemcpy(h_freq.data(), freq, sizeof(unsigned long long) * npat, cudaMemcpyDeviceToHost));
+  HPCCG_CUDA_DROP(cudaMemcpy(h_val.data(), pat_val, sizeof(double) * h_val.size(), cudaMemcpyDeviceToHost));
+  HPCCG_CUDA_DROP(cudaMemcpy(h_delta.data(), pat_delta, sizeof(int) * h_delta.size(), cudaMemcpyDeviceToHost));
+  HPCCG_CUDA_DROP(cudaMemcpy(h_len.data(), pat_len, sizeof(int) * npat, cudaMemcpyDeviceToHost));
+  int top = 0;
+  for (int i = 1; i < npat; ++i)
+    if (h_freq[i] > h_freq[top]) top = i;
+  if (top != 0) {
+    for (int j = 0; j < m->slots; ++j) {
+      std::swap(h_val[j], h_val[(size_t)top * m->slots + j]);
+      std::swap(h_delta[j], h_delta[(size_t)top * m->slots + j]);
     }
-    int k = 0;
-    for (long long sl = 0; sl < nslices; ++sl)
-      if (raw_flags[sl]) {
-        raw_index[sl] = k;
-        cudaMemcpyAsync(raw_vals + (size_t)k * per_slice, m->vals + sl * per_slice, sizeof(double) * per_slice, cudaMemcpyDeviceToDevice, nullptr);
-        cudaMemcpyAsync(raw_cols + (size_t)k * per_slice, m->cols + sl * per_slice, sizeof(int) * per_slice, cudaMemcpyDeviceToDevice, nullptr);
-        ++k;
-      }
+    std::swap(h_len[0], h_len[top]);
+    HPCCG_CUDA_DROP(cudaMemcpy(pat_val, h_val.data(), sizeof(double) * h_val.size(), cudaMemcpyHostToDevice));
+    HPCCG_CUDA_DROP(cudaMemcpy(pat_delta, h_delta.data(), sizeof(int) * h_delta.size(), cudaMemcpyHostToDevice));
+    HPCCG_CUDA_DROP(cudaMemcpy(pat_len, h_len.data(), sizeof(int) * npat, cudaMemcpyHostToDevice));
   }
-  cudaError_t e = cudaMemcpy(slice_raw, raw_index.data(), sizeof(int) * nslices, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) {
-    cudaFree(raw_vals);
-    cudaFree(raw_cols);
+  pattern_verify_kernel<<<grid, kThreads>>>(m->vals, m->cols, m->slots, m->n, pat_id, 0, top, pat_val, pat_delta, pat_len, scal + 2);
+  count_launch();
+  HPCCG_CUDA_DROP(cudaGetLastError());
+  HPCCG_CUDA_DROP(cudaMemcpy(h_scal, scal, sizeof h_scal, cudaMemcpyDeviceToHost));
+  if (h_scal[2]) {  // a hash collision merged two different patterns: keep the uncompressed matrix
     drop();
-    return fail_cuda(e, "dictionary encode", __FILE__, __LINE__);
+    return 0;
   }
 #undef HPCCG_CUDA_DROP
+  std::memset(&m->pattern0, 0, sizeof m->pattern0);
+  for (int j = 0; j < m->slots; ++j) {
+    m->pattern0.value[j] = h_val[j];
+    m->pattern0.delta[j] = h_delta[j];
+  }
+  m->pattern0.len = h_len[0];
+  cudaFree(keys);
+  cudaFree(freq);
+  cudaFree(ids);
+  cudaFree(scal);
+  cudaFree(rep);
   cudaFree(m->vals);
   cudaFree(m->cols);
   m->vals = nullptr;
   m->cols = nullptr;
-  m->codes = codes;
-  m->dict = dict;
-  m->ndict = ndict;
-  m->raw_index = slice_raw;
-  m->raw_vals = raw_vals;
-  m->raw_cols = raw_cols;
-  m->nraw = (int)nraw;
+  m->pat_id = pat_id;
+  m->pat_val = pat_val;
+  m->pat_delta = pat_delta;
+  m->pat_len = pat_len;
+  m->npat = npat;
   m->format = 1;
   return 0;
 }

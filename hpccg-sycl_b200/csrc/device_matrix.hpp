@@ -25,18 +25,17 @@ struct hpccg_dev_matrix {
   int *cols = nullptr;
 
   // format 1 (hpccg_dev_matrix_compress): vals/cols are released and replaced by
-  //   codes     : uint8 [slices][slots][128]   one byte per stored entry (same SELL-C addressing as vals/cols)
-  //   dict      : DictEntry[256]               (value, column - row) pairs, matrix-wide
-  //   raw_index : int32 [slices]               -1 = coded slice, else index of the slice in raw_vals / raw_cols
-  //   raw_vals / raw_cols : [nraw][slots][128] the few slices whose pairs are not all in the table
+  //   pat_id    : uint16 [npad]           pattern id of every row (0xFFFF in the padding tail)
+  //   pat_val   : double [npat][slots]    the stored values of each pattern, in the reference's order
+  //   pat_delta : int32  [npat][slots]    column id minus row id of each stored entry
+  //   pat_len   : int32  [npat]           stored entries of the pattern (row length)
   int format = 0;
-  unsigned char *codes = nullptr;
-  hpccg::DictEntry *dict = nullptr;
-  int ndict = 0;
-  int *raw_index = nullptr;
-  double *raw_vals = nullptr;
-  int *raw_cols = nullptr;
-  int nraw = 0;
+  unsigned short *pat_id = nullptr;
+  double *pat_val = nullptr;
+  int *pat_delta = nullptr;
+  int *pat_len = nullptr;
+  int npat = 0;
+  hpccg::Pattern0 pattern0;             // host copy of pattern 0, passed to the SpMV kernel as a __grid_constant__ parameter
 
   // rows [0,interior_begin) and [interior_end,n) may reference halo columns (>= n); rows in between do not
   int interior_begin = 0, interior_end = 0;

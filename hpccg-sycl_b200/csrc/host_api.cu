@@ -281,7 +281,7 @@ int wanted_format() {
   const int f = ctx().matrix_format;
   if (f >= 0) return f;
   const char *e = std::getenv("HPCCG_B200_FORMAT");
-  return (e && std::string(e) == "dict") ? 1 : 0;
+  return (e && std::string(e) == "pattern") ? 1 : 0;
 }
 
 int get_mirror(HPC_Sparse_Matrix *A, hpccg_dev_matrix **out) {
@@ -756,7 +756,7 @@ int hpccg_api_set_options(int stencil, int host_arrays) {
 }
 
 int hpccg_api_set_matrix_format(int format) {
-  if (format != 0 && format != 1) return fail(HPCCG_ERR_ARG, "matrix format must be 0 (SELL int32) or 1 (dictionary-coded)");
+  if (format != 0 && format != 1) return fail(HPCCG_ERR_ARG, "matrix format must be 0 (SELL int32) or 1 (pattern-coded)");
   ctx().matrix_format = format;
   return 0;
 }

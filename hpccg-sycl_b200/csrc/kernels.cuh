@@ -463,73 +463,45 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
   }
 }
 
-// ---- dictionary-compressed SpMV (opt-in format) ------------------------------------------------
-// Same pipeline as spmv_sell_tma_kernel, but a stage is SPS slices of one-byte CODES (SLOTS x 128 bytes per slice,
-// 27x less than values + column ids); the (value, column - row) table sits in shared memory.  The arithmetic is the
-// same un-contracted mul/add in slot order on the same values, so the result is bit-identical to the SELL path.
-// Slices flagged in raw_index (pairs outside the table) are read uncompressed from raw_vals / raw_cols.
-template <int SLOTS, int SPS, int NSTAGES>
-struct SpmvDictCfg {
-  static constexpr int kRows = SPS * kSliceRows;
-  static constexpr int kStageBytes = SLOTS * kRows;  // one byte per entry
-  static constexpr int kSmemBytes = NSTAGES * kStageBytes + kDictSize * (int)sizeof(DictEntry) + NSTAGES * 8 + 64;
-};
-
-template <int SLOTS, int SPS, int NSTAGES, bool DOT>
-__global__ void __launch_bounds__(SPS *kSliceRows, 3)
-spmv_dict_tma_kernel(const unsigned char *__restrict__ codes, const DictEntry *__restrict__ dict,
-                     const int *__restrict__ raw_index, const double *__restrict__ raw_vals,
-                     const int *__restrict__ raw_cols, const double *__restrict__ x, double *__restrict__ y, int n,
-                     int row_begin, int row_end, int stage_begin, int stage_end, double *partials, int partial_offset,
-                     int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo) {
-  using Cfg = SpmvDictCfg<SLOTS, SPS, NSTAGES>;
-  constexpr int kRows = Cfg::kRows;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char *sc = smem_raw;
-  DictEntry *sd = reinterpret_cast<DictEntry *>(smem_raw + NSTAGES * Cfg::kStageBytes);
-  unsigned long long *bars =
-      reinterpret_cast<unsigned long long *>(smem_raw + NSTAGES * Cfg::kStageBytes + kDictSize * sizeof(DictEntry));
-  __shared__ double red[kRows / 32];
+// ---- pattern-coded SpMV (opt-in format) -------------------------------------------------------
+// One 16-bit pattern id per row instead of 12 bytes per stored entry: HPC_sparsemv reads 2 + 16 bytes per row.
+//   * warp-uniform fast path (every lane's row has pattern 0, the most frequent one): the pattern's values and deltas
+//     are constant-bank operands (Pattern0 is a __grid_constant__ parameter, the loops are fully unrolled), so a stored
+//     entry costs an add, an address computation, the gather of x, a multiply and an add -- no matrix load at all;
+//   * otherwise each lane reads its pattern's entries from the pattern table (L1/L2-resident, broadcast when lanes
+//     share a pattern).
+// The arithmetic is the same un-contracted mul/add in stored order on the same values: bit-identical to the SELL paths.
+// Rows are walked in tiles of kThreads rows, persistent CTAs; with a PeerLink the tiles are rotated (interior first) and a
+// CTA waits for the neighbours' halo stamps only when it reaches a tile that references halo columns.
+template <int SLOTS, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_pattern_kernel(const unsigned short *__restrict__ pat_id, const double *__restrict__ pat_val,
+                    const int *__restrict__ pat_delta, const int *__restrict__ pat_len,
+                    const __grid_constant__ Pattern0 p0, const double *__restrict__ x, double *__restrict__ y, int n,
+                    int row_begin, int row_end, int tile_begin, int tile_end, double *partials, int partial_offset,
+                    int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo) {
+  __shared__ double smem[kThreads / 32];
   if (fp.check_active && fp.st->active == 0) return;
-
   const int tid = threadIdx.x;
-  const int T = stage_end - stage_begin;
-  const int my_count = (int)blockIdx.x < T ? (T - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int T = tile_end - tile_begin;
   int rot = 0;
   if (halo.link) {
-    const int s0 = (halo.interior_begin + kRows - 1) / kRows - stage_begin;
+    const int s0 = (halo.interior_begin + kThreads - 1) / kThreads - tile_begin;
     rot = (s0 > 0 && s0 < T) ? s0 : 0;
   }
-  auto phys = [&](int i) {
-    int g = (int)blockIdx.x + i * (int)gridDim.x + rot;
-    if (g >= T) g -= T;
-    return stage_begin + g;
-  };
-  unsigned long long policy = 0;
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGES; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  }
-  for (int e = tid; e < kDictSize; e += kRows) sd[e] = dict[e];
-  __syncthreads();
-  auto issue = [&](int i) {
-    const int st = i % NSTAGES;
-    const long long stage = phys(i);
-    mbar_expect_tx(bars + st, Cfg::kStageBytes);
-    tma_bulk_g2s(sc + (size_t)st * Cfg::kStageBytes, codes + stage * Cfg::kStageBytes, Cfg::kStageBytes, bars + st, policy);
-  };
-  if (tid == 0)
-    for (int i = 0; i < NSTAGES && i < my_count; ++i) issue(i);
-
-  const int soff = (tid / kSliceRows) * SLOTS * kSliceRows + (tid % kSliceRows);
   double dot = 0.0;
   bool halo_ready = (halo.link == nullptr);
-  for (int i = 0; i < my_count; ++i) {
-    const int st = i % NSTAGES;
-    const int stage = phys(i);
-    const int row = stage * kRows + tid;
-    const bool touches_halo = halo.link && (stage * kRows < halo.interior_begin || (stage + 1) * kRows > halo.interior_end);
+  const bool fast_ok = (p0.len == SLOTS);  // the unrolled fast path assumes a full row
+  int it = 0;
+  for (int g0 = blockIdx.x; g0 < T; g0 += gridDim.x, ++it) {
+    int g = g0 + rot;
+    if (g >= T) g -= T;
+    const int tile = tile_begin + g;
+    // The warps of a CTA run through the tiles without synchronising.  Rows at the ends of a grid line take the slower
+    // table path, and they sit at fixed positions of a tile, so the warp -> 32-row-group assignment is rotated from tile
+    // to tile; otherwise the same two warps would do all the slow rows and the other six would wait for them at the end.
+    const int row = tile * kThreads + ((tid + 32 * it) & (kThreads - 1));
+    const bool touches_halo = halo.link && (tile * kThreads < halo.interior_begin || (tile + 1) * kThreads > halo.interior_end);
     if (touches_halo && !halo_ready) {
       if (tid < halo.link->nnb) {
         const Mailbox *own = halo.link->box[halo.link->rank];
@@ -538,110 +510,169 @@ spmv_dict_tma_kernel(const unsigned char *__restrict__ codes, const DictEntry *_
       __syncthreads();
       halo_ready = true;
     }
-    const int raw = __ldg(raw_index + stage * SPS + tid / kSliceRows);  // uniform over the 4 warps of a slice
-    mbar_wait(bars + st, (unsigned)(i / NSTAGES) & 1u);
+    const bool in_range = row >= row_begin && row < row_end;  // row_end <= n
+    const int pid = in_range ? (int)pat_id[row] : 0xFFFF;
     double sum = 0.0;
-    if (raw < 0) {
-      const unsigned char *c = sc + (size_t)st * Cfg::kStageBytes + soff;
-      const int rowc = min(row, n - 1);  // rows of the padding tail carry only padding codes: keep their dummy gather in range
-      // the row is walked in chunks of CH slots: CH gathers in flight per thread, and few enough registers for three
-      // resident CTAs (24 warps) per SM -- this kernel is bound by instruction issue and L1, not by HBM
+    if (fast_ok && __all_sync(0xffffffffu, pid == 0) && !touches_halo) {
+      // every lane's row is a full-length pattern-0 row: values and deltas are constant-bank operands, no predicates
+      // (a divergent per-lane version of this test measured 4 % slower at 512^3 and 19 % slower at 256^3)
+      double xv[SLOTS];
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) xv[j] = __ldg(x + (row + p0.delta[j]));
+#pragma unroll
+      for (int j = 0; j < SLOTS; ++j) sum = __dadd_rn(sum, __dmul_rn(p0.value[j], xv[j]));
+    } else if (pid != 0xFFFF) {
+      const int len = __ldg(pat_len + pid);
+      const double *pv = pat_val + (size_t)pid * SLOTS;
+      const int *pd = pat_delta + (size_t)pid * SLOTS;
       constexpr int CH = (SLOTS % 9 == 0) ? 9 : SLOTS;
 #pragma unroll
       for (int j0 = 0; j0 < SLOTS; j0 += CH) {
-        int cb[CH];
-        int cj[CH];
         double vj[CH], xv[CH];
 #pragma unroll
-        for (int j = 0; j < CH; ++j) cb[j] = c[(j0 + j) * kSliceRows];
-#pragma unroll
         for (int j = 0; j < CH; ++j) {
-          // one 128-bit shared-memory load per entry: {value, delta}; the padding code maps to {0.0, 0}
-          const int4 e = *reinterpret_cast<const int4 *>(sd + cb[j]);
-          vj[j] = __hiloint2double(e.y, e.x);
-          cj[j] = rowc + e.z;
-        }
-        if (!touches_halo) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) xv[j] = __ldg(x + cj[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) xv[j] = cj[j] >= halo.n ? __ldcg(x + cj[j]) : __ldg(x + cj[j]);
+          const bool live = j0 + j < len;
+          const int c = live ? row + __ldg(pd + j0 + j) : row;
+          vj[j] = live ? __ldg(pv + j0 + j) : 0.0;
+          xv[j] = (touches_halo && c >= halo.n) ? __ldcg(x + c) : __ldg(x + c);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const double t = __dadd_rn(sum, __dmul_rn(vj[j], xv[j]));
-          sum = cb[j] != kCodePadding ? t : sum;
-        }
-      }
-    } else {
-      // uncompressed slice (a handful per matrix: e.g. the two plane rows whose halo numbering is interleaved)
-      const long long o = ((long long)raw * SLOTS) * kSliceRows + (tid % kSliceRows);
-#pragma unroll 1
-      for (int j = 0; j < SLOTS; ++j) {
-        const int cc = raw_cols[o + j * kSliceRows];
-        if (cc >= 0) {
-          const double xx = (halo.link && cc >= halo.n) ? __ldcg(x + cc) : __ldg(x + cc);
-          sum = __dadd_rn(sum, __dmul_rn(raw_vals[o + j * kSliceRows], xx));
+          sum = j0 + j < len ? t : sum;
         }
       }
     }
-    if (row >= row_begin && row < row_end) {
+    if (in_range) {
       y[row] = sum;
       if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + row), sum));
     }
-    __syncthreads();
-    if (tid == 0 && i + NSTAGES < my_count) issue(i + NSTAGES);
   }
   if (DOT) {
-    const int lane = tid & 31, warp = tid >> 5;
-    double w = warp_sum(dot);
-    if (lane == 0) red[warp] = w;
-    __syncthreads();
-    double total = 0.0;
-    if (warp == 0) {
-      total = lane < kRows / 32 ? red[lane] : 0.0;
-      total = warp_sum(total);
-    }
-    publish_and_finish_n<kRows>(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, red);
+    const double total = block_sum(dot, smem);
+    publish_and_finish(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, smem);
   }
 }
 
-// Encoder: one thread per row; looks every stored (value, column - row) pair up in the table and writes its code.
-__global__ void __launch_bounds__(kThreads)
-dict_encode_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, long long npad,
-                   const DictEntry *__restrict__ dict, int ndict, unsigned char *__restrict__ codes,
-                   int *__restrict__ slice_raw) {
-  __shared__ long long s_val[kDictSize];
-  __shared__ int s_delta[kDictSize];
-  for (int e = threadIdx.x; e < ndict; e += kThreads) {
-    s_val[e] = __double_as_longlong(dict[e].value);
-    s_delta[e] = dict[e].delta;
+// ---- pattern encoder (one-off, hpccg_dev_matrix_compress) ---------------------------------------------------------
+__device__ __forceinline__ unsigned long long pattern_hash(const double *__restrict__ vals, const int *__restrict__ cols,
+                                                           long long row, int slots, int *len_out) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  int len = 0;
+  for (int j = 0; j < slots; ++j) {
+    const long long o = sell_offset(row, j, slots);
+    const int c = cols[o];
+    if (c < 0) continue;
+    ++len;
+    h = (h ^ (unsigned long long)__double_as_longlong(vals[o])) * 0xff51afd7ed558ccdull;
+    h ^= h >> 32;
+    h = (h ^ (unsigned long long)(unsigned int)(c - (int)row) ^ ((unsigned long long)j << 40)) * 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 29;
   }
-  __syncthreads();
-  for (long long row = (long long)blockIdx.x * kThreads + threadIdx.x; row < npad; row += (long long)gridDim.x * kThreads) {
-    int last = 0;  // neighbouring entries of a row usually sit next to each other in the table
+  *len_out = len;
+  h ^= (unsigned long long)len << 56;
+  return h | 1ull;  // 0 is the empty key
+}
+
+// Pass A: every row claims (or finds) the slot of its pattern hash in an open-addressing table.
+__global__ void __launch_bounds__(kThreads)
+pattern_insert_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, int n,
+                      unsigned long long *keys, unsigned mask, int *overflow) {
+  for (long long row = (long long)blockIdx.x * kThreads + threadIdx.x; row < n; row += (long long)gridDim.x * kThreads) {
+    int len;
+    const unsigned long long h = pattern_hash(vals, cols, row, slots, &len);
+    unsigned slot = (unsigned)(h >> 17) & mask;
+    int probes = 0;
+    for (;;) {
+      const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + slot);
+      if (k == h) break;
+      if (k == 0) {
+        const unsigned long long old = atomicCAS(keys + slot, 0ull, h);
+        if (old == 0 || old == h) break;
+      }
+      slot = (slot + 1) & mask;
+      if (++probes > 256) {
+        *overflow = 1;
+        break;
+      }
+    }
+  }
+}
+
+// Pass B: occupied slots get consecutive ids.
+__global__ void __launch_bounds__(kThreads)
+pattern_number_kernel(const unsigned long long *__restrict__ keys, unsigned table_size, int *ids, int *count) {
+  for (unsigned s = blockIdx.x * kThreads + threadIdx.x; s < table_size; s += gridDim.x * kThreads)
+    ids[s] = keys[s] ? atomicAdd(count, 1) : -1;
+}
+
+// Pass C: rows look their id up, leave a representative row per id and count the rows per id (warp-aggregated).
+__global__ void __launch_bounds__(kThreads)
+pattern_assign_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, int n, long long npad,
+                      const unsigned long long *__restrict__ keys, const int *__restrict__ ids, unsigned mask,
+                      unsigned short *__restrict__ pat_id, int *rep_row, unsigned long long *freq) {
+  for (long long base = (long long)blockIdx.x * kThreads; base < npad; base += (long long)gridDim.x * kThreads) {
+    const long long row = base + threadIdx.x;
+    int id = -1;
+    if (row < n) {
+      int len;
+      const unsigned long long h = pattern_hash(vals, cols, row, slots, &len);
+      unsigned slot = (unsigned)(h >> 17) & mask;
+      while (keys[slot] != h) slot = (slot + 1) & mask;
+      id = ids[slot];
+      rep_row[id] = (int)row;  // any row of the pattern will do (verified afterwards)
+    }
+    if (row < npad) pat_id[row] = id >= 0 ? (unsigned short)id : (unsigned short)0xFFFF;
+    const unsigned peers = __match_any_sync(__activemask(), id);
+    if (id >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(freq + id, (unsigned long long)__popc(peers));
+  }
+}
+
+// Pass D: the pattern table from the representative rows.
+__global__ void __launch_bounds__(kThreads)
+pattern_fill_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, int npat,
+                    const int *__restrict__ rep_row, double *pat_val, int *pat_delta, int *pat_len) {
+  for (int id = blockIdx.x * kThreads + threadIdx.x; id < npat; id += gridDim.x * kThreads) {
+    const long long row = rep_row[id];
+    int len = 0;
     for (int j = 0; j < slots; ++j) {
       const long long o = sell_offset(row, j, slots);
       const int c = cols[o];
-      int code = kCodePadding;
-      if (c >= 0) {
-        const long long vb = __double_as_longlong(vals[o]);
-        const int d = (int)(c - row);
-        code = kCodeMissing;
-        for (int t = 0; t < ndict; ++t) {
-          int e = last + t;
-          if (e >= ndict) e -= ndict;
-          if (s_val[e] == vb && s_delta[e] == d) {
-            code = e;
-            last = e;
-            break;
-          }
-        }
-        if (code == kCodeMissing) slice_raw[row / kSliceRows] = 1;
-      }
-      codes[o] = (unsigned char)code;
+      if (c < 0) continue;
+      pat_val[(size_t)id * slots + len] = vals[o];
+      pat_delta[(size_t)id * slots + len] = c - (int)row;
+      ++len;
     }
+    pat_len[id] = len;
+    for (int j = len; j < slots; ++j) {
+      pat_val[(size_t)id * slots + j] = 0.0;
+      pat_delta[(size_t)id * slots + j] = 0;
+    }
+  }
+}
+
+// Pass E: exact check of every row against its pattern (a 64-bit hash collision must not corrupt the matrix), with the
+// final relabelling (the most frequent pattern becomes id 0) applied on the fly.
+__global__ void __launch_bounds__(kThreads)
+pattern_verify_kernel(const double *__restrict__ vals, const int *__restrict__ cols, int slots, int n,
+                      unsigned short *__restrict__ pat_id, int swap_a, int swap_b, const double *__restrict__ pat_val,
+                      const int *__restrict__ pat_delta, const int *__restrict__ pat_len, int *mismatch) {
+  for (long long row = (long long)blockIdx.x * kThreads + threadIdx.x; row < n; row += (long long)gridDim.x * kThreads) {
+    int id = pat_id[row];
+    if (id == swap_a) id = swap_b;
+    else if (id == swap_b) id = swap_a;
+    pat_id[row] = (unsigned short)id;
+    int len = 0;
+    bool ok = true;
+    for (int j = 0; j < slots; ++j) {
+      const long long o = sell_offset(row, j, slots);
+      const int c = cols[o];
+      if (c < 0) continue;
+      ok = ok && len < slots && __double_as_longlong(pat_val[(size_t)id * slots + len]) == __double_as_longlong(vals[o]) &&
+           pat_delta[(size_t)id * slots + len] == c - (int)row;
+      ++len;
+    }
+    if (!ok || len != pat_len[id]) *mismatch = 1;
   }
 }
 

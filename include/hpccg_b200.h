@@ -102,13 +102,13 @@ int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int 
 int hpccg_dev_matrix_bytes(const hpccg_dev_matrix *m, long long *bytes);
 
 /* Optional lossless re-encoding of the mirror (SURVEY.md 8 f3 "traffic reduction beyond the algorithmic figure"):
- * every stored entry becomes a one-byte code into a matrix-wide table of distinct (value, column - row) pairs, so
- * HPC_sparsemv streams slots + 16 bytes per row instead of 12*slots + 16.  Same values, same summation order:
- * results are bit-identical to the default format.  Slices that use a pair outside the 254-entry table stay
- * uncompressed; a matrix that does not compress is left as it is (format 0) and the call still returns 0. */
+ * a row's PATTERN is its sequence of stored (value, column - row) pairs; the mirror keeps one 16-bit pattern id per
+ * row plus the table of distinct patterns, so HPC_sparsemv streams 2 + 16 bytes per row instead of 12*slots + 16.
+ * Same values, same columns, same summation order: results are bit-identical to the default format.  A matrix with
+ * more than 65535 distinct patterns does not compress and is left as it is (format 0); the call still returns 0. */
 int hpccg_dev_matrix_compress(hpccg_dev_matrix *m);
-/* format: 0 = SELL-C values + int32 column ids (default, the north-star layout), 1 = dictionary-coded. */
-int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *dict_entries, int *raw_slices);
+/* format: 0 = SELL-C values + int32 column ids (default, the north-star layout), 1 = pattern-coded. */
+int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *patterns);
 
 /* ------------------------------------------------------------------------------------------------
  * Kernels (device pointers, asynchronous on `stream` = cudaStream_t or NULL)
@@ -173,7 +173,7 @@ int hpccg_api_set_options(int stencil, int host_arrays);
 /* HPCCG() prints "Initial Residual" / "Iteration = k   Residual" on rank 0 like HPCCG.cpp:356,372-373; 0 silences it. */
 int hpccg_api_set_print(int on);
 /* Format of the device mirrors created from now on by this thread: 0 (default) or 1 (hpccg_dev_matrix_compress is applied
- * when the mirror is built).  The environment variable HPCCG_B200_FORMAT=dict selects 1 when this was never called. */
+ * when the mirror is built).  The environment variable HPCCG_B200_FORMAT=pattern selects 1 when this was never called. */
 int hpccg_api_set_matrix_format(int format);
 /* generate_matrix.hpp:58 */
 int hpccg_api_generate_matrix(int nx, int ny, int nz, void **A, double **x, double **b, double **xexact);

@@ -1,6 +1,6 @@
-"""-m gpu: the opt-in dictionary-coded matrix format (hpccg_dev_matrix_compress).  It is a lossless
-re-encoding -- one byte per stored entry into a table of (value, column - row) pairs, uncompressed "raw" slices where a
-pair is not in the table -- so every result must be BIT-IDENTICAL to the default SELL format and to the reference."""
+"""-m gpu: the opt-in pattern-coded matrix format (hpccg_dev_matrix_compress).  It is a lossless
+re-encoding -- one 16-bit id per row into a table of distinct row patterns (sequences of (value, column - row) pairs)
+-- so every result must be BIT-IDENTICAL to the default SELL format and to the reference."""
 import ctypes as C
 
 import numpy as np
@@ -18,7 +18,7 @@ def seeded(n, seed):
 
 @pytest.fixture()
 def dict_format(H):
-    H.set_matrix_format("dict")
+    H.set_matrix_format("pattern")
     yield
     H.set_matrix_format("sell")
 
@@ -35,10 +35,11 @@ def test_sparsemv_bit_exact_and_mirror_identical(H, refwrap, cuda, dims, stencil
     bytes0 = m.bytes()
     f = m.compress()
     if slots in (27, 7):
-        assert f["format"] == 1 and f["raw_slices"] == 0 and 1 <= f["dict_entries"] <= slots
+        # a 27-pt block has at most 3*3*3 boundary types, a 7-pt block the same (each of x, y, z: first / inner / last)
+        assert f["format"] == 1 and 1 <= f["patterns"] <= 27
         assert m.bytes() < bytes0 / 6
     else:
-        assert f["format"] == 0  # thin blocks (fewer slots) have no dictionary kernel: left as they are
+        assert f["format"] == 0  # thin blocks (fewer slots) have no pattern kernel: left as they are
     v1, c1 = m.download()
     assert np.array_equal(c0, c1) and np.array_equal(v0, v1)
     n = A.local_nrow
@@ -77,8 +78,8 @@ def test_hpccg_dict_format_matches_reference_and_sell_bitwise(H, refwrap, cuda, 
 
 @pytest.mark.parametrize("dims,size,stencil", [((16, 16, 8), 2, 27), ((12, 10, 2), 3, 27), ((32, 32, 16), 4, 27), ((8, 8, 4), 2, 7)])
 def test_multi_rank_dict_format_with_halo_columns(H, refwrap, cuda, dict_format, dims, size, stencil):
-    """Halo columns (>= local_nrow) get their own table entries; the plane rows whose halo numbering is interleaved
-    (first-encounter order) do not fit the table and stay raw."""
+    """Rows that reference halo columns (>= local_nrow) have their own patterns; the two plane rows whose halo numbering
+    is interleaved (first-encounter order) get one pattern per row."""
     torch = cuda
     mats = _build_ranks(H, dims, size, stencil, True)
     ms = [A.device() for A in mats]
@@ -131,18 +132,25 @@ def _spmv_rows(nnz, vals, cols, x):
     return y
 
 
-def test_partly_compressible_matrix_keeps_raw_slices(H, refwrap, cuda):
-    """The reference's 20x30x10 matrix with some entries perturbed: perturbed slices stay raw, result still exact."""
+def test_perturbed_matrix_gets_more_patterns(H, refwrap, cuda):
+    """The reference's 20x30x10 matrix with 64 rows perturbed: 64 more patterns, result still exact."""
     torch = cuda
     with refwrap.RefWorld(20, 30, 10, variant=ref_variant()) as R:
         nnz, vals, cols = R.array(0, "nnz_in_row"), R.array(0, "list_of_vals").copy(), R.array(0, "list_of_inds")
     rng = np.random.default_rng(3)
     starts = np.concatenate([[0], np.cumsum(nnz)[:-1]])
-    for row in (5, 700, 701, 3000, 5999):          # rows in 4 different slices get unique values
+    m0, keep0 = _create_from_rows(H, nnz, vals, cols, 6000)
+    base = m0.compress()["patterns"]
+    m0.destroy()
+    for row in list(range(0, 16)) + list(range(700, 716)) + list(range(3000, 3016)) + list(range(5984, 6000)):
         vals[starts[row]:starts[row] + nnz[row]] = rng.uniform(-2, 2, nnz[row])
     m, keep = _create_from_rows(H, nnz, vals, cols, 6000)
+    v0, c0 = m.download()
     f = m.compress()
-    assert f["format"] == 1 and f["raw_slices"] == 4, f
+    # 64 new patterns; the few original patterns whose only rows were perturbed (the two corner rows) disappear
+    assert f["format"] == 1 and base + 56 <= f["patterns"] <= base + 64, (f, base)
+    v1, c1 = m.download()
+    assert np.array_equal(v0, v1) and np.array_equal(c0, c1)
     x = seeded(6000, 11)
     xd = torch.from_numpy(x).cuda()
     yd = torch.empty(6000, dtype=torch.float64, device="cuda")
@@ -152,9 +160,9 @@ def test_partly_compressible_matrix_keeps_raw_slices(H, refwrap, cuda):
 
 
 def test_incompressible_matrix_is_left_alone(H, cuda):
-    """Random values: (almost) every slice would be raw, so compress() leaves the matrix in format 0 (not an error)."""
+    """70 000 random rows = 70 000 patterns > 65535 ids: compress() leaves the matrix in format 0 (not an error)."""
     torch = cuda
-    n = 1000
+    n = 70000
     rng = np.random.default_rng(5)
     nnz = np.full(n, 7, dtype=np.int32)
     vals = rng.uniform(-1, 1, 7 * n)
@@ -164,5 +172,9 @@ def test_incompressible_matrix_is_left_alone(H, cuda):
     x = seeded(n, 1)
     yd = torch.empty(n, dtype=torch.float64, device="cuda")
     H.dev.spmv(m, torch.from_numpy(x).cuda(), yd)
-    assert np.array_equal(yd.cpu().numpy(), _spmv_rows(nnz, vals, cols, x))
+    ref = (vals.reshape(n, 7) * x[cols.reshape(n, 7)])
+    acc = np.zeros(n)
+    for j in range(7):
+        acc = acc + ref[:, j]
+    assert np.array_equal(yd.cpu().numpy(), acc)
     m.destroy()
