@@ -33,8 +33,12 @@ def main():
     cases = [((16, 16, 8), 27, True), ((5, 4, 3), 7, True), ((12, 10, 1), 27, True), ((64, 64, 16), 27, True),
              ((64, 64, 16), 27, False), ((96, 80, 24), 27, False), ((64, 64, 16), 7, False)]
     # every case twice: halos + scalar sums through peer memory inside the kernels (default), then the NCCL path
-    for comm, (dims, stencil, host_rows) in [(c, k) for c in ("p2p", "nccl") for k in cases]:
+    runs = [(c, "sell", k) for c in ("p2p", "nccl") for k in cases]
+    # the opt-in pattern-coded mirror through both communication paths
+    runs += [(c, "pattern", k) for c in ("p2p", "nccl") for k in (cases[0], cases[4], cases[6])]
+    for comm, fmt, (dims, stencil, host_rows) in runs:
         os.environ["HPCCG_B200_COMM"] = comm  # read when the matrix's peer link is created (first solve)
+        H.set_matrix_format(fmt)
         H.set_options(stencil, host_rows)
         A = H.generate_matrix(*dims)
         H.make_local_matrix(A)
@@ -64,7 +68,7 @@ def main():
         scale = sum(float(np.abs(xs[r][:nrow[r]] * ys[r]).sum()) for r in range(size))
         assert abs(d - dref) <= 1e-12 * scale, (d, dref)
         res = H.compute_residual(n, x, A.xexact)
-        result["cases"].append({"dims": dims, "stencil": stencil, "host_rows": host_rows, "niters": niters, "comm": comm,
+        result["cases"].append({"dims": dims, "stencil": stencil, "host_rows": host_rows, "niters": niters, "comm": comm, "format": fmt,
                                 "worst_rel": float(worst), "residual": float(res), "ddot_rel": abs(d - dref) / scale})
         A.destroy()
     hdist.finalize()
