@@ -7,10 +7,10 @@
 
 #include "cg_state.hpp"
 
-// HBM layout of one rank's matrix and solver workspace:
-//   vals  : double [slots][npad]   column-major ELLPACK, slot j = j-th stored entry of the row
-//   cols  : int32  [slots][npad]   local column id, -1 = padding (masked, never multiplied)
-//   npad  : local_nrow rounded up to 512 rows (one tile of the 2-rows-per-thread SpMV)
+// HBM layout of one rank's matrix and solver workspace (DESIGN.md section 2):
+//   vals  : double [npad/128][slots][128]  SELL-C (C = 128, sigma = 1), slot j = j-th stored entry of the row
+//   cols  : int32  [npad/128][slots][128]  local column id, -1 = padding (masked, never multiplied)
+//   npad  : local_nrow rounded up to 512 rows
 //   r, Ap : double [npad] ; p : double [ncol_pad]  (solver temporaries, HPCCG.cpp:327-329)
 //   partials : double [kMaxPartials] block partials of the deterministic reductions
 //   state : CgState (device scalars) ; hist : double [hist_cap] residual history

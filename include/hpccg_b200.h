@@ -68,9 +68,10 @@ int hpccg_nccl_init(const void *id128, int rank, int size);
 int hpccg_nccl_finalize(void);
 
 /* ------------------------------------------------------------------------------------------------
- * Device matrix: column-major ELLPACK mirror of HPC_Sparse_Matrix (HPC_Sparse_Matrix.hpp:54-85)
- *   vals[slot][row_padded] (fp64), cols[slot][row_padded] (int32, -1 = padding), slot j = the j-th
- *   STORED entry of the row, so the summation order of HPC_sparsemv.cpp:83-86 is preserved.
+ * Device matrix: SELL-C (C = 128 rows per slice, sigma = 1) mirror of HPC_Sparse_Matrix (HPC_Sparse_Matrix.hpp:54-85)
+ *   vals[slice][slot][128] (fp64), cols[slice][slot][128] (int32, -1 = padding), slot j = the j-th
+ *   STORED entry of the row, so the summation order of HPC_sparsemv.cpp:83-86 is preserved.  A slice is one
+ *   contiguous block, which is what the TMA bulk copies of the SpMV kernel move.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct hpccg_dev_matrix hpccg_dev_matrix;
 
@@ -95,7 +96,8 @@ int hpccg_dev_matrix_set_halo(hpccg_dev_matrix *m, int num_neighbors, const int 
 
 int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m);
 
-/* Introspection (tests compare the device ELL of both construction routes bit for bit). */
+/* Introspection (tests compare the device matrix of both construction routes bit for bit; download returns the
+ * canonical column-major [slots][padded_rows] view whatever the device format is). */
 int hpccg_dev_matrix_info(const hpccg_dev_matrix *m, int *local_nrow, int *local_ncol, int *slots,
                           long long *padded_rows);
 int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int *cols_host); /* slots*padded_rows each */
