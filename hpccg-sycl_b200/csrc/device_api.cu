@@ -215,6 +215,17 @@ static bool use_tma_path(int slots) {
   return mode == 1 && (slots == 27 || slots == 7);
 }
 
+// L2 prefetch distance of the TMA SpMV in stages (0 = off); HPCCG_B200_L2_AHEAD overrides for A/B runs.
+static int tma_l2_ahead() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = std::getenv("HPCCG_B200_L2_AHEAD");
+    v = e ? std::atoi(e) : 0;
+    if (v < 0 || v > 64) v = 0;
+  }
+  return v;
+}
+
 template <int SLOTS, int SPS, int NSTAGES, bool DOT>
 static int tma_ctas_per_sm() {
   static int cached = 0;
@@ -252,7 +263,7 @@ static int launch_tma_t(const hpccg_dev_matrix *m, const double *x, double *y, c
   const int sb = pl.row_begin / rows;
   spmv_sell_tma_kernel<SLOTS, SPS, NSTAGES, DOT><<<pl.grid, rows, Cfg::kSmemBytes, s>>>(
       m->vals, m->cols, x, y, pl.row_begin, pl.row_end, sb, sb + pl.tiles, m->partials, partial_offset, total_partials,
-      &m->state->counter, fp, halo);
+      &m->state->counter, fp, halo, tma_l2_ahead());
   count_launch();
   HPCCG_LAUNCH_CHECK();
   return 0;

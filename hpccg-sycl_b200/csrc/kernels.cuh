@@ -343,6 +343,10 @@ struct SpmvHalo {
   int interior_end;
 };
 
+__device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 template <int SLOTS, int SPS, int NSTAGES>
 struct SpmvTmaCfg {
   static constexpr int kRows = SPS * kSliceRows;            // rows per stage = threads per CTA
@@ -355,7 +359,7 @@ template <int SLOTS, int SPS, int NSTAGES, bool DOT>
 __global__ void __launch_bounds__(SPS *kSliceRows, 1)
 spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ cols, const double *__restrict__ x,
                      double *__restrict__ y, int row_begin, int row_end, int stage_begin, int stage_end, double *partials,
-                     int partial_offset, int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo) {
+                     int partial_offset, int total_partials, unsigned *counter, FinishParams fp, SpmvHalo halo, int l2_ahead) {
   using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
   constexpr int kRows = Cfg::kRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -393,6 +397,12 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
     mbar_expect_tx(bars + st, Cfg::kValBytes + Cfg::kColBytes);
     tma_bulk_g2s(sv + (size_t)st * SLOTS * kRows, vals + stage * SLOTS * kRows, Cfg::kValBytes, bars + st, policy);
     tma_bulk_g2s(sc + (size_t)st * SLOTS * kRows, cols + stage * SLOTS * kRows, Cfg::kColBytes, bars + st, policy);
+    // optional: pull the stage `l2_ahead` turns later into L2 now, so DRAM sees requests beyond the shared-memory ring
+    if (l2_ahead > 0 && i + l2_ahead < my_count) {
+      const long long ahead = phys(i + l2_ahead);
+      tma_prefetch_l2(vals + ahead * SLOTS * kRows, Cfg::kValBytes);
+      tma_prefetch_l2(cols + ahead * SLOTS * kRows, Cfg::kColBytes);
+    }
   };
   if (tid == 0)
     for (int i = 0; i < NSTAGES && i < my_count; ++i) issue(i);
