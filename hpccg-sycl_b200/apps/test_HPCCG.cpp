@@ -10,13 +10,25 @@
 //   --tolerance T  reference hard-codes 0.0 (main.cpp:188)
 //   --device-only  build the matrix directly in HBM (needed beyond 430^3, where the reference's int local_nnz overflows)
 //   --check        compute_residual(x, xexact) after the solve (the call the reference has commented out, main.cpp:310-316)
+//   --ranks N      what `mpirun -np N test_HPCCG nx ny nz` is for the reference's -DUSING_MPI build: the driver forks N
+//                  processes, one per GPU, ranks stacked in z (nx ny nz stay the LOCAL block).  The MPI negotiation of
+//                  make_local_matrix becomes a file-based allgather in a scratch directory, the CG loop talks over
+//                  NVLink peer memory / NCCL; rank 0 prints the report with the reference's MPI-only blocks.
 //   extra YAML block "B200" with GFLOP/s, HBM GB/s of the CG loop and its fraction of the roofline.
 // Mode 2 (matrix file, read_HPC_row) is deprecated upstream (README.md:114-118) and not supported.
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "HPCCG.hpp"
 #include "HPC_Sparse_Matrix.hpp"
@@ -24,13 +36,85 @@
 #include "compute_residual.hpp"
 #include "generate_matrix.hpp"
 #include "hpccg_b200.h"
+#include "make_local_matrix.hpp"
 #include "mytimer.hpp"
 
 using std::cerr;
 using std::cout;
 using std::endl;
 
+// ---- set-up collective of a --ranks job: every rank drops its contribution as a file and reads the others' --------
+struct FileWorld {
+  std::string dir;
+  int rank = 0, size = 1;
+  long seq = 0;
+};
+
+static int file_allgather(void *user, const void *send, long long nbytes, void *recv) {
+  FileWorld *w = static_cast<FileWorld *>(user);
+  const long k = w->seq++;
+  auto name = [&](int r) { return w->dir + "/ag_" + std::to_string(k) + "_" + std::to_string(r); };
+  {
+    const std::string tmp = name(w->rank) + ".tmp";
+    std::ofstream f(tmp.c_str(), std::ios::binary);
+    f.write(static_cast<const char *>(send), nbytes);
+    f.close();
+    if (std::rename(tmp.c_str(), name(w->rank).c_str()) != 0) return 1;
+  }
+  for (int r = 0; r < w->size; ++r) {
+    struct stat st;
+    int waited_ms = 0;
+    while (stat(name(r).c_str(), &st) != 0 || st.st_size != nbytes) {
+      usleep(500);
+      if (++waited_ms > 240000) return 2;  // 2 minutes: a rank died
+    }
+    std::ifstream f(name(r).c_str(), std::ios::binary);
+    f.read(static_cast<char *>(recv) + (size_t)r * nbytes, nbytes);
+    if (!f) return 3;
+  }
+  return 0;
+}
+
+static int run_rank(int argc, char *argv[], FileWorld *world);
+
 int main(int argc, char *argv[]) {
+  int ranks = 1;
+  for (int i = 1; i + 1 < argc; ++i)
+    if (std::string(argv[i]) == "--ranks") ranks = std::atoi(argv[i + 1]);
+  if (ranks <= 1) return run_rank(argc, argv, nullptr);
+  // the parent creates no CUDA context before fork(): every child picks its own GPU
+  char tmpl[] = "/tmp/hpccg_b200_XXXXXX";
+  if (!mkdtemp(tmpl)) {
+    cerr << "cannot create a scratch directory for the rank rendezvous" << endl;
+    return 1;
+  }
+  std::vector<pid_t> kids;
+  for (int r = 0; r < ranks; ++r) {
+    const pid_t pid = fork();
+    if (pid == 0) {
+      FileWorld w;
+      w.dir = tmpl;
+      w.rank = r;
+      w.size = ranks;
+      const int rc = run_rank(argc, argv, &w);
+      _exit(rc);
+    }
+    kids.push_back(pid);
+  }
+  int worst = 0;
+  for (pid_t pid : kids) {
+    int status = 0;
+    waitpid(pid, &status, 0);
+    const int rc = WIFEXITED(status) ? WEXITSTATUS(status) : 128;
+    if (rc > worst) worst = rc;
+  }
+  const std::string rm = std::string("rm -rf ") + tmpl;
+  if (std::system(rm.c_str()) != 0) cerr << "could not remove " << tmpl << endl;
+  return worst;
+}
+
+static int run_rank(int argc, char *argv[], FileWorld *world) {
+  const int rank = world ? world->rank : 0, size = world ? world->size : 1;
   HPC_Sparse_Matrix *A;
   double *x, *b, *xexact;
   double times[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -44,14 +128,16 @@ int main(int argc, char *argv[]) {
     else if (a == "--stencil" && i + 1 < argc) stencil = std::atoi(argv[++i]);
     else if (a == "--tolerance" && i + 1 < argc) tolerance = std::atof(argv[++i]);
     else if (a == "--peak" && i + 1 < argc) peak_gbs = std::atof(argv[++i]);
+    else if (a == "--ranks" && i + 1 < argc) ++i;
     else if (a == "--device-only") device_only = 1;
     else if (a == "--check") check = 1;
     else if (ndims < 3 && a[0] != '-') dims[ndims++] = std::atoi(argv[i]);
     else ndims = -1000;
   }
   if (ndims != 3) {
+    if (rank == 0)
     cerr << "Usage:" << endl
-         << "Mode 1: " << argv[0] << " nx ny nz [--iters N] [--stencil 27|7] [--tolerance T] [--device-only] [--check]" << endl
+         << "Mode 1: " << argv[0] << " nx ny nz [--iters N] [--stencil 27|7] [--tolerance T] [--device-only] [--check] [--ranks N]" << endl
          << "     where nx, ny and nz are the local sub-block dimensions." << endl
          << "Mode 2 (HPC_data_file) of the reference is deprecated upstream and not supported." << endl;
     return 1;
@@ -59,12 +145,45 @@ int main(int argc, char *argv[]) {
   const int nx = dims[0], ny = dims[1], nz = dims[2];
   const long long n = (long long)nx * ny * nz;
   if (27 * n > 2147483647LL) device_only = 1;
+  (void)argc;
   if (hpccg_api_set_options(stencil, device_only ? 0 : 1)) {
     cerr << hpccg_last_error() << endl;
     return 1;
   }
+  if (world) {
+    // what MPI_Init + MPI_Comm_rank/size are for the reference (main.cpp:131-132 hard-codes 0/1 in this fork)
+    int ngpu = 0;
+    if (hpccg_device_count(&ngpu) || ngpu < 1) {
+      cerr << "rank " << rank << ": " << hpccg_last_error() << endl;
+      return 1;
+    }
+    if (size > ngpu) {
+      if (rank == 0) cerr << "--ranks " << size << " needs " << size << " GPUs, this node has " << ngpu << endl;
+      return 3;
+    }
+    if (hpccg_set_device(rank) || hpccg_ctx_set(rank, size) || hpccg_ctx_set_allgather(file_allgather, world)) {
+      cerr << "rank " << rank << ": " << hpccg_last_error() << endl;
+      return 1;
+    }
+    char id[128], all[128 * 64];
+    std::memset(id, 0, sizeof id);
+    if (size > 64) return 1;
+    if (rank == 0 && hpccg_nccl_unique_id(id)) {
+      cerr << hpccg_last_error() << endl;
+      return 1;
+    }
+    if (file_allgather(world, id, 128, all) || hpccg_nccl_init(all, rank, size)) {
+      cerr << "rank " << rank << ": NCCL rendezvous failed: " << hpccg_last_error() << endl;
+      return 1;
+    }
+  }
 
   generate_matrix(nx, ny, nz, &A, &x, &b, &xexact);
+  if (world) {
+    const double t6 = mytimer();
+    make_local_matrix(A);  // main.cpp:179-180
+    times[6] = mytimer() - t6;
+  }
 
   int niters = 0;
   double normr = 0.0;
@@ -72,7 +191,7 @@ int main(int argc, char *argv[]) {
   int ierr = HPCCG(A, b, x, max_iter, tolerance, niters, normr, times);
   const auto end = std::chrono::high_resolution_clock::now();
   const std::chrono::duration<double> elapsed = end - start;
-  cout << "Elapsed time: " << elapsed.count() << " s\n";
+  if (rank == 0) cout << "Elapsed time: " << elapsed.count() << " s\n";
   if (ierr) cerr << "Error in call to CG: " << ierr << ": " << hpccg_last_error() << ".\n" << endl;
   // second solve: the first one paid for the one-off mirror build and workspace allocation inside times[0]
   double times2[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -84,14 +203,38 @@ int main(int argc, char *argv[]) {
   const double fniters = niters, fnrow = A->total_nrow, fnnz = (double)A->total_nnz;
   const double fnops_ddot = fniters * 4 * fnrow, fnops_waxpby = fniters * 6 * fnrow, fnops_sparsemv = fniters * 2 * fnnz;
   const double fnops = fnops_ddot + fnops_waxpby + fnops_sparsemv;
-  const double *t = ierr ? times : times2;
+  double *t = ierr ? times : times2;
+  t[6] = times[6];
+  // main.cpp:202-210: min / max / avg of the DDOT all-reduce time over the ranks
+  double t4stats[3] = {t[4], t[4], t[4]};
+  if (world) {
+    std::vector<double> all(size);
+    if (file_allgather(world, &t[4], sizeof(double), all.data()) == 0) {
+      t4stats[2] = 0.0;
+      for (double v : all) {
+        t4stats[0] = std::min(t4stats[0], v);
+        t4stats[1] = std::max(t4stats[1], v);
+        t4stats[2] += v / size;
+      }
+    }
+  }
+  double residual = 0;
+  if (check && compute_residual(A->local_nrow, x, xexact, &residual))  // collective: every rank calls it (MPI_MAX in the reference)
+    cerr << "Error in call to compute_residual: " << hpccg_last_error() << endl;
+  if (rank != 0) {
+    destroyMatrix(A);
+    free_vectors(x, b, xexact);
+    hpccg_nccl_finalize();
+    return ierr ? 2 : 0;
+  }
 
   YAML_Doc doc("hpccg", "1.0");
   doc.add("Parallelism", "");
-  doc.get("Parallelism")->add("MPI not enabled", "");
+  if (world) doc.get("Parallelism")->add("Number of MPI ranks", size);  // ranks are GPU processes here
+  else doc.get("Parallelism")->add("MPI not enabled", "");
   doc.get("Parallelism")->add("OpenMP not enabled", "");
   doc.get("Parallelism")->add("SYCL not enabled", "");
-  doc.get("Parallelism")->add("Number of B200 GPUs", 1);
+  doc.get("Parallelism")->add("Number of B200 GPUs", size);
   doc.add("Dimensions", "");
   doc.get("Dimensions")->add("nx", nx);
   doc.get("Dimensions")->add("ny", ny);
@@ -114,6 +257,21 @@ int main(int argc, char *argv[]) {
   doc.get("MFLOPS Summary")->add("DDOT    ", fnops_ddot / t[1] / 1.0E6);
   doc.get("MFLOPS Summary")->add("WAXPBY  ", fnops_waxpby / t[2] / 1.0E6);
   doc.get("MFLOPS Summary")->add("SPARSEMV", fnops_sparsemv / (t[3]) / 1.0E6);
+  if (world) {  // main.cpp:284-298
+    doc.add("DDOT Timing Variations", "");
+    doc.get("DDOT Timing Variations")->add("Min DDOT MPI_Allreduce time", t4stats[0]);
+    doc.get("DDOT Timing Variations")->add("Max DDOT MPI_Allreduce time", t4stats[1]);
+    doc.get("DDOT Timing Variations")->add("Avg DDOT MPI_Allreduce time", t4stats[2]);
+    const double totalSparseMVTime = t[3] + t[5] + t[6];
+    doc.add("SPARSEMV OVERHEADS", "");
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV MFLOPS W OVERHEAD", fnops_sparsemv / (totalSparseMVTime) / 1.0E6);
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Time", (t[5] + t[6]));
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Pct", (t[5] + t[6]) / totalSparseMVTime * 100.0);
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Setup Time", (t[6]));
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Setup Pct", (t[6]) / totalSparseMVTime * 100.0);
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Time", (t[5]));
+    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Pct", (t[5]) / totalSparseMVTime * 100.0);
+  }
   // B200 block: the kernel times above are CUDA-event sums, fused kernels split by algorithmic bytes
   const double kernel_s = t[1] + t[2] + t[3];
   const double bytes_per_row = (stencil == 7 ? 7 : 27) * 12.0 + 16.0 + 72.0;
@@ -127,15 +285,12 @@ int main(int argc, char *argv[]) {
   doc.get("B200")->add("CG kernels HBM GB/s", fniters * bytes_per_row * (double)n / kernel_s / 1.0E9);
   doc.get("B200")->add("Fraction of HBM roofline", fniters * bytes_per_row * (double)n / kernel_s / 1.0E9 / peak_gbs);
   doc.get("B200")->add("HBM roofline GB/s", peak_gbs);
-  if (check) {
-    double residual = 0;
-    if (compute_residual(A->local_nrow, x, xexact, &residual)) cerr << "Error in call to compute_residual: " << hpccg_last_error() << endl;
-    doc.get("B200")->add("Difference between computed and exact", residual);
-  }
+  if (check) doc.get("B200")->add("Difference between computed and exact", residual);
   const std::string yaml = doc.generateYAML();
   cout << yaml;
 
   destroyMatrix(A);
   free_vectors(x, b, xexact);
+  if (world) hpccg_nccl_finalize();
   return ierr ? 2 : 0;
 }

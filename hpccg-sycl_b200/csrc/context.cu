@@ -175,6 +175,7 @@ int nccl_allgather_host(const void *send, long long nbytes, void *recv) {
 struct PeerCard {  // what every rank publishes about itself
   cudaIpcMemHandle_t mailbox, p;
   int ok;                 // this rank could allocate / export
+  int pci[3];             // domain, bus, device of this rank's GPU: two ranks on one GPU must never wait for each other in a kernel
   int n, nnb;
   int neighbors[kMaxPeerNb], recv_length[kMaxPeerNb], send_length[kMaxPeerNb];
 };
@@ -204,6 +205,18 @@ int peer_link_create(hpccg_dev_matrix *m) {
       mine.ok = 0;
     }
   }
+  {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+      mine.pci[0] = prop.pciDomainID;
+      mine.pci[1] = prop.pciBusID;
+      mine.pci[2] = prop.pciDeviceID;
+    } else {
+      cudaGetLastError();
+      mine.ok = 0;
+    }
+  }
   mine.n = m->n;
   mine.nnb = m->num_neighbors;
   for (int i = 0; i < m->num_neighbors && i < kMaxPeerNb; ++i) {
@@ -216,6 +229,11 @@ int peer_link_create(hpccg_dev_matrix *m) {
   HPCCG_TRY(nccl_allgather_host(&mine, sizeof mine, cards.data()));
   bool all_ok = true;
   for (const PeerCard &c : cards) all_ok = all_ok && c.ok;
+  // Kernels of different ranks wait for each other through the mailboxes; that is only safe when every rank has its
+  // own GPU (two waiting kernels on one GPU are not guaranteed to run concurrently).
+  for (int a = 0; a < R && all_ok; ++a)
+    for (int b = a + 1; b < R; ++b)
+      if (std::memcmp(cards[a].pci, cards[b].pci, sizeof cards[a].pci) == 0) all_ok = false;
 
   PeerLink h;
   std::memset(&h, 0, sizeof h);

@@ -40,3 +40,22 @@ def test_cli_7pt_device_only_and_usage(H, cuda, tmp_path):
     assert "Number of iterations: 39\n" in res.stdout and "Stencil points: 7" in res.stdout
     assert run([], tmp_path).returncode == 1
     assert "Usage:" in run(["4", "4"], tmp_path).stderr
+
+
+def test_cli_ranks_mode(H, cuda, tmp_path):
+    """`test_HPCCG nx ny nz --ranks N` = the reference's `mpirun -np N` run: one process per GPU, rank 0 prints the report
+    with the MPI-only blocks (main.cpp:284-298).  On a box with fewer GPUs than ranks it must refuse (two ranks on one GPU
+    would wait for each other inside kernels)."""
+    ngpu = cuda.cuda.device_count()
+    res = run(["16", "16", "8", "--ranks", str(ngpu + 1)], tmp_path)
+    assert res.returncode == 3 and "needs" in res.stderr
+    if ngpu < 2:
+        pytest.skip("needs 2 GPUs for the positive case")
+    res = run(["32", "32", "16", "--ranks", "2", "--check"], tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = res.stdout
+    assert "Number of MPI ranks: 2\n" in out and "Number of iterations: 149\n" in out
+    assert "DDOT Timing Variations: \n" in out and "SPARSEMV OVERHEADS: \n" in out
+    assert out.count("Initial Residual = ") == 1  # rank 0 only
+    m = re.search(r"Difference between computed and exact: (\S+)", out)
+    assert m and float(m.group(1)) <= 1e-12

@@ -131,6 +131,40 @@ def test_fused_update_and_p_update(H, refwrap, cuda, n):
     assert np.array_equal(p.cpu().numpy(), refwrap.waxpby(1.0, rr, beta, ph, variant=var))
 
 
+@pytest.mark.parametrize("dims,stencil", [((20, 30, 10), 27), ((33, 17, 5), 7), ((130, 3, 2), 27), ((7, 5, 3), 27)])
+@pytest.mark.parametrize("fmt", ["sell", "pattern"])
+def test_spmv_stays_inside_its_arrays(H, refwrap, cuda, dims, stencil, fmt):
+    """compute-sanitizer is closed on this pool, so bounds are checked by poisoning: y carries a sentinel tail that
+    must survive (no store beyond local_nrow, although the kernels work on rows padded to 512), and x carries a NaN
+    tail right after local_ncol that must never reach a result (padding slots gather x[0] and are discarded)."""
+    torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(stencil, True)
+    H.set_matrix_format(fmt)
+    A = H.generate_matrix(*dims)
+    H.set_matrix_format("sell")
+    m = A.device()
+    n = A.local_nrow
+    xh = seeded(n, 99)
+    x = torch.full((n + 1024,), float("nan"), dtype=torch.float64, device="cuda")
+    x[:n] = torch.from_numpy(xh).cuda()
+    y = torch.full((n + 1024,), -7.25, dtype=torch.float64, device="cuda")
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    with refwrap.RefWorld(*dims, stencil=stencil, variant=ref_variant()) as R:
+        yr = R.spmv([xh.copy()])[0]
+    for fused in (False, True):
+        y.fill_(-7.25)
+        if fused:
+            H.dev.spmv_dot(m, x, y, res)
+            assert np.isfinite(res.item())
+        else:
+            H.dev.spmv(m, x, y)
+        yh = y.cpu().numpy()
+        assert np.array_equal(yh[:n], yr)
+        assert (yh[n:] == -7.25).all()
+    A.destroy()
+
+
 def test_compute_residual(H, cuda):
     n = 5001
     a, b = seeded(n, 7), seeded(n, 8)
