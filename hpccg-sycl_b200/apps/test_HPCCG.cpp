@@ -97,6 +97,9 @@ int main(int argc, char *argv[]) {
       w.rank = r;
       w.size = ranks;
       const int rc = run_rank(argc, argv, &w);
+      std::cout.flush();
+      std::cerr.flush();
+      std::fflush(nullptr);
       _exit(rc);
     }
     kids.push_back(pid);
