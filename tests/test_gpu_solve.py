@@ -118,6 +118,23 @@ def test_tolerance_exit_matches_reference(H, refwrap, cuda):
     A.destroy()
 
 
+@pytest.mark.parametrize("max_iter", [0, 1, 2, 3, 17])
+def test_short_iteration_counts(H, refwrap, cuda, max_iter):
+    """`for (k = 1; k < max_iter && normr > tolerance; k++)` (HPCCG.cpp:358): max_iter <= 1 runs no iteration, niters = 0,
+    normr = the initial residual, x untouched; otherwise max_iter - 1 iterations."""
+    H.set_rank(0, 1)
+    H.set_options(27, True)
+    A = H.generate_matrix(12, 9, 7)
+    x = A.x.copy()
+    niters, normr, _, hist = H.HPCCG(A, A.b, x, max_iter, 0.0)
+    with refwrap.RefWorld(12, 9, 7, variant=ref_variant()) as R:
+        ref = R.solve(max_iter)
+    assert niters == ref["niters"] == max(max_iter - 1, 0)
+    assert abs(normr - ref["normr"]) <= 1e-12 * ref["normr"]
+    assert np.allclose(x, ref["x"][0], rtol=1e-12, atol=1e-14)
+    A.destroy()
+
+
 def test_degenerate_sizes(H, refwrap, cuda):
     """1x1x1 converges exactly (normr underflows to 0 and the loop exits)."""
     for dims in ((1, 1, 1), (7, 1, 1), (2, 2, 1)):
