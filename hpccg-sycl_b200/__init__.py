@@ -33,7 +33,7 @@ __all__ = [
     "yaml_report", "run_local_world", "launch_count", "dev",
 ]
 
-SOLVE_DEFAULT, SOLVE_UNFUSED, SOLVE_NO_OVERLAP, SOLVE_TIMERS = 0, 1, 2, 4
+SOLVE_DEFAULT, SOLVE_UNFUSED, SOLVE_NO_OVERLAP, SOLVE_TIMERS, SOLVE_NCCL_ONLY, SOLVE_GRAPH = 0, 1, 2, 4, 8, 16
 
 
 def _ptr(v) -> int:

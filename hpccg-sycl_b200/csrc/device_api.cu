@@ -701,6 +701,8 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->scratch_x);
   cudaFree(m->scratch_y);
   peer_link_destroy(m);
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->graph_stream) cudaStreamDestroy(m->graph_stream);
   if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
   if (m->ev_p_ready) cudaEventDestroy(m->ev_p_ready);
   if (m->ev_halo_done) cudaEventDestroy(m->ev_halo_done);
@@ -1090,8 +1092,23 @@ static int exchange_halo(std::vector<SolveRank> &rk, int R, bool nccl, double *c
   return 0;
 }
 
+// capture_only: the launches are being recorded into a CUDA graph (stream capture): no event timing, no host polling,
+// no read-back -- solve_readback() runs after the graph has been launched.
+static int solve_readback(hpccg_dev_matrix *m, int max_iter, int *niters_out, double *normr_out, double *hist_host,
+                          CgState *hs_out, cudaStream_t s) {
+  CgState hs;
+  HPCCG_CUDA(cudaMemcpyAsync(&hs, m->state, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+  if (hist_host) HPCCG_CUDA(cudaMemcpyAsync(hist_host, m->hist, sizeof(double) * max_iter, cudaMemcpyDeviceToHost, s));
+  HPCCG_CUDA(cudaStreamSynchronize(s));
+  if (niters_out) *niters_out = hs.niters;
+  if (normr_out) *normr_out = hs.normr;
+  if (hs_out) *hs_out = hs;
+  return 0;
+}
+
 static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_iter, double tol, int *niters_out,
-                         double *normr_out, double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t s) {
+                         double *normr_out, double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t s,
+                         bool capture_only = false) {
   const int L = (int)rk.size();
   const bool multi = R > 1;
   const bool unfused = (flags & HPCCG_SOLVE_UNFUSED) != 0;
@@ -1120,8 +1137,10 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   timers.on = (flags & HPCCG_SOLVE_TIMERS) != 0 && times != nullptr;
   timers.s = s;
   cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
-  HPCCG_CUDA(cudaEventCreate(&ev_loop0));
-  HPCCG_CUDA(cudaEventCreate(&ev_loop1));
+  if (!capture_only) {
+    HPCCG_CUDA(cudaEventCreate(&ev_loop0));
+    HPCCG_CUDA(cudaEventCreate(&ev_loop1));
+  }
   double t4_host = 0.0;
 
   std::vector<double *> pv(L);
@@ -1232,9 +1251,9 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   if (multi) HPCCG_TRY(finish_multi(FIN_INIT, 0, max_iter <= 1, false));
 
   // ---- iterations (HPCCG.cpp:358-386) ----
-  HPCCG_CUDA(cudaEventRecord(ev_loop0, s));
+  if (!capture_only) HPCCG_CUDA(cudaEventRecord(ev_loop0, s));
   int *h_active = nullptr;
-  if (tol > 0.0) HPCCG_CUDA(cudaMallocHost(&h_active, sizeof(int)));
+  if (tol > 0.0 && !capture_only) HPCCG_CUDA(cudaMallocHost(&h_active, sizeof(int)));
   for (int k = 1; k < max_iter; ++k) {
     const int last = (k + 1 == max_iter) ? 1 : 0;
     if (unfused && k > 1) {
@@ -1332,22 +1351,19 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       if (*h_active == 0) break;
     }
   }
+  if (capture_only) return 0;
   HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
   if (h_active) cudaFreeHost(h_active);
 
   // ---- results ----
   CgState hs;
-  HPCCG_CUDA(cudaMemcpyAsync(&hs, rk[0].m->state, sizeof(CgState), cudaMemcpyDeviceToHost, s));
-  if (hist_host) HPCCG_CUDA(cudaMemcpyAsync(hist_host, rk[0].m->hist, sizeof(double) * max_iter, cudaMemcpyDeviceToHost, s));
-  HPCCG_CUDA(cudaStreamSynchronize(s));
+  HPCCG_TRY(solve_readback(rk[0].m, max_iter, niters_out, normr_out, hist_host, &hs, s));
   if (p2p) {
     int perr = 0;
     HPCCG_CUDA(cudaMemcpy(&perr, &link->error, sizeof(int), cudaMemcpyDeviceToHost));
     if (perr) return fail(HPCCG_ERR_COMM, "peer-memory wait timed out (%s): a rank of the job did not arrive",
                           perr == 2 ? "halo" : "scalar reduction");
   }
-  if (niters_out) *niters_out = hs.niters;
-  if (normr_out) *normr_out = hs.normr;
   float ms = 0.f;
   HPCCG_CUDA(cudaEventElapsedTime(&ms, ev_loop0, ev_loop1));
   if (loop_ms) *loop_ms = ms;
@@ -1388,7 +1404,62 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
     return cg_solve_impl(rk, c.size, true, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags,
                          (cudaStream_t)stream);
   }
-  return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+  if (!(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
+    return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+
+  // ---- CUDA-graph replay (launch-bound sizes): the launch sequence of a solve depends only on this key ----
+  if (max_iter < 1) max_iter = 1;
+  const bool same = m->graph_b == b && m->graph_x == x && m->graph_max_iter == max_iter && m->graph_tol == tolerance &&
+                    m->graph_flags == flags;
+  if (!same) {  // first solve with this key runs directly; a second one is worth a capture
+    if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+    m->graph_exec = nullptr;
+    m->graph_b = b;
+    m->graph_x = x;
+    m->graph_max_iter = max_iter;
+    m->graph_tol = tolerance;
+    m->graph_flags = flags;
+    return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+  }
+  if (!m->graph_stream) HPCCG_CUDA(cudaStreamCreateWithFlags(&m->graph_stream, cudaStreamNonBlocking));
+  cudaStream_t gs = m->graph_stream;
+  if (!m->graph_exec) {
+    HPCCG_TRY(ensure_solver_workspace(m, max_iter, 1));
+    HPCCG_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    int rc = cg_solve_impl(rk, 1, false, max_iter, tolerance, nullptr, nullptr, nullptr, nullptr, nullptr, flags, gs, true);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(gs, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    e = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      m->graph_exec = nullptr;
+      return fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    }
+  }
+  // order the replay after whatever the caller enqueued on its stream (b, x uploads), and time it as a whole
+  cudaEvent_t ev_in = nullptr, ev0 = nullptr, ev1 = nullptr;
+  HPCCG_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  HPCCG_CUDA(cudaEventCreate(&ev0));
+  HPCCG_CUDA(cudaEventCreate(&ev1));
+  HPCCG_CUDA(cudaEventRecord(ev_in, (cudaStream_t)stream));
+  HPCCG_CUDA(cudaStreamWaitEvent(gs, ev_in, 0));
+  HPCCG_CUDA(cudaEventRecord(ev0, gs));
+  HPCCG_CUDA(cudaGraphLaunch(m->graph_exec, gs));
+  count_launch(3 * (max_iter - 1) + 4);
+  HPCCG_CUDA(cudaEventRecord(ev1, gs));
+  HPCCG_TRY(solve_readback(m, max_iter, niters, normr, hist_host, nullptr, gs));
+  float ms = 0.f;
+  HPCCG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  if (loop_ms) *loop_ms = ms;
+  cudaEventDestroy(ev_in);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return 0;
 }
 
 int hpccg_dev_cg_solve_group(int nranks, hpccg_dev_matrix *const *m, const double *const *b, double *const *x, int max_iter,

@@ -60,6 +60,14 @@ struct hpccg_dev_matrix {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_p_ready = nullptr, ev_halo_done = nullptr;
 
+  // CUDA-graph replay of a whole solve (HPCCG_SOLVE_GRAPH): the launch sequence is a function of this key only
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  const double *graph_b = nullptr;
+  double *graph_x = nullptr;
+  int graph_max_iter = 0, graph_flags = 0;
+  double graph_tol = 0.0;
+
   // peer-memory link (multi-process runs on one NVSwitch domain): mailbox in this rank's HBM, IPC-mapped views of
   // the peers' mailboxes and of the neighbours' p vectors; peer_link == nullptr: NCCL send/recv + gathers are used
   hpccg::Mailbox *mailbox = nullptr;

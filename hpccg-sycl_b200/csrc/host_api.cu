@@ -721,7 +721,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   // time of a launch-bound solve (20x30x10: 43 -> 12 us per iteration).  Below 2^20 rows a single-rank solve therefore
   // records only the loop time and splits it over times[1..3] by the kernels' algorithmic byte counts.
   const bool event_timers = ctx().size > 1 || m->n >= (1 << 20) || std::getenv("HPCCG_B200_TIMERS") != nullptr;
-  int flags = event_timers ? HPCCG_SOLVE_TIMERS : 0;
+  int flags = event_timers ? HPCCG_SOLVE_TIMERS : HPCCG_SOLVE_GRAPH;  // launch-bound sizes: replay repeated solves as a graph
   if (const char *e = std::getenv("HPCCG_B200_UNFUSED"))
     if (e[0] == '1') flags |= HPCCG_SOLVE_UNFUSED;
   int it = 0;

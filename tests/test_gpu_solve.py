@@ -135,6 +135,43 @@ def test_short_iteration_counts(H, refwrap, cuda, max_iter):
     A.destroy()
 
 
+def test_graph_replay_of_repeated_solves_is_bit_identical(H, refwrap, cuda):
+    """HPCCG_SOLVE_GRAPH (what HPCCG() uses below 2^20 rows): the first solve with a key runs directly, the second is
+    captured into a CUDA graph, later ones replay it.  Same kernels, same grids, same reduction trees -> same bits."""
+    torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(27, True)
+    A = H.generate_matrix(20, 30, 10)
+    with refwrap.RefWorld(20, 30, 10, variant=ref_variant()) as R:
+        ref = R.solve(150)
+    hists = []
+    for _ in range(4):  # direct, capture + launch, replay, replay
+        x = A.x.copy()
+        niters, normr, times, hist = H.HPCCG(A, A.b, x, 150, 0.0)
+        check_history(hist, ref["hist"], niters, ref["niters"])
+        check_solution(x, ref["x"][0])
+        assert times[0] > 0 and times[3] > 0
+        hists.append(hist)
+    for h in hists[1:]:
+        assert np.array_equal(h, hists[0], equal_nan=True)
+    # a different max_iter is a different key: direct again, then captured again
+    for _ in range(3):
+        x = A.x.copy()
+        niters, normr, _, hist = H.HPCCG(A, A.b, x, 40, 0.0)
+        assert niters == 39 and np.array_equal(hist[:40], hists[0][:40])
+    # device pointers through the C-ABI, tolerance exit inside a replayed graph
+    m = A.device()
+    b = torch.from_numpy(A.b.copy()).cuda()
+    xd = torch.zeros(A.local_nrow, dtype=torch.float64, device="cuda")
+    with refwrap.RefWorld(20, 30, 10, variant=ref_variant()) as R:
+        rt = R.solve(150, 1e-6)
+    for _ in range(3):
+        xd.zero_()
+        out = H.dev.cg_solve(m, b, xd, 150, 1e-6, flags=H.SOLVE_GRAPH)
+        assert out["niters"] == rt["niters"] and abs(out["normr"] - rt["normr"]) <= 1e-8 * rt["normr"]
+    A.destroy()
+
+
 def test_degenerate_sizes(H, refwrap, cuda):
     """1x1x1 converges exactly (normr underflows to 0 and the loop exits)."""
     for dims in ((1, 1, 1), (7, 1, 1), (2, 2, 1)):
