@@ -28,8 +28,8 @@ from . import _capi
 from ._capi import HpccgError, check, lib
 
 __all__ = [
-    "HpccgError", "Matrix", "DeviceMatrix", "set_matrix_format", "set_rank", "get_rank", "set_options", "set_print", "generate_matrix",
-    "make_local_matrix", "HPCCG", "HPC_sparsemv", "ddot", "waxpby", "exchange_externals", "compute_residual",
+    "HpccgError", "Matrix", "DeviceMatrix", "set_matrix_format", "set_rank", "get_rank", "set_options", "set_print", "generate_matrix", "read_HPC_row",
+    "read_HPC_row", "make_local_matrix", "HPCCG", "HPC_sparsemv", "ddot", "waxpby", "exchange_externals", "compute_residual",
     "yaml_report", "run_local_world", "launch_count", "dev",
 ]
 
@@ -196,6 +196,16 @@ def generate_matrix(nx: int, ny: int, nz: int) -> Matrix:
     x, b, e = _capi.PD(), _capi.PD(), _capi.PD()
     check(lib.hpccg_api_generate_matrix(nx, ny, nz, C.byref(A), C.byref(x), C.byref(b), C.byref(e)), "generate_matrix")
     n = nx * ny * nz
+    views = [np.ctypeslib.as_array(p, shape=(n,)) for p in (x, b, e)]
+    return Matrix(A.value, views[0], views[1], views[2], (x, b, e))
+
+
+def read_HPC_row(data_file) -> Matrix:
+    """read_HPC_row.cpp:217-373: the matrix, x, b and xexact of this rank from the reference's text format."""
+    A = C.c_void_p()
+    x, b, e = _capi.PD(), _capi.PD(), _capi.PD()
+    check(lib.hpccg_api_read_HPC_row(str(data_file).encode(), C.byref(A), C.byref(x), C.byref(b), C.byref(e)), "read_HPC_row")
+    n = int(lib.hpccg_api_matrix_scalar(A.value, b"local_nrow"))
     views = [np.ctypeslib.as_array(p, shape=(n,)) for p in (x, b, e)]
     return Matrix(A.value, views[0], views[1], views[2], (x, b, e))
 

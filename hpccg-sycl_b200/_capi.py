@@ -68,6 +68,7 @@ SIGNATURES = {
     "hpccg_api_set_print": (C.c_int, [C.c_int]),
     "hpccg_api_set_matrix_format": (C.c_int, [C.c_int]),
     "hpccg_api_generate_matrix": (C.c_int, [C.c_int, C.c_int, C.c_int, PVP, C.POINTER(PD), C.POINTER(PD), C.POINTER(PD)]),
+    "hpccg_api_read_HPC_row": (C.c_int, [C.c_char_p, PVP, C.POINTER(PD), C.POINTER(PD), C.POINTER(PD)]),
     "hpccg_api_make_local_matrix": (C.c_int, [VP]),
     "hpccg_api_HPCCG": (C.c_int, [VP, VP, VP, C.c_int, C.c_double, PI, PD, PD]),
     "hpccg_api_HPC_sparsemv": (C.c_int, [VP, VP, VP]),

@@ -15,7 +15,8 @@
 //                  make_local_matrix becomes a file-based allgather in a scratch directory, the CG loop talks over
 //                  NVLink peer memory / NCCL; rank 0 prints the report with the reference's MPI-only blocks.
 //   extra YAML block "B200" with GFLOP/s, HBM GB/s of the CG loop and its fraction of the roofline.
-// Mode 2 (matrix file, read_HPC_row) is deprecated upstream (README.md:114-118) and not supported.
+// Mode 2, `test_HPCCG HPC_data_file` (read_HPC_row; deprecated upstream, README.md:114-118), is supported as well; the
+// reference prints uninitialised nx/ny/nz in that mode (main.cpp:252-254), here nx = total rows, ny = nz = 1.
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -38,6 +39,7 @@
 #include "hpccg_b200.h"
 #include "make_local_matrix.hpp"
 #include "mytimer.hpp"
+#include "read_HPC_row.hpp"
 
 using std::cerr;
 using std::cout;
@@ -122,6 +124,7 @@ static int run_rank(int argc, char *argv[], FileWorld *world) {
   double *x, *b, *xexact;
   double times[7] = {0, 0, 0, 0, 0, 0, 0};
   int dims[3] = {0, 0, 0}, ndims = 0;
+  std::string data_file;
   int max_iter = 150, stencil = 27, device_only = 0, check = 0;
   double tolerance = 0.0;
   double peak_gbs = 6543.7;  // measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json); --peak overrides
@@ -134,20 +137,23 @@ static int run_rank(int argc, char *argv[], FileWorld *world) {
     else if (a == "--ranks" && i + 1 < argc) ++i;
     else if (a == "--device-only") device_only = 1;
     else if (a == "--check") check = 1;
+    else if (ndims == 0 && data_file.empty() && a[0] != '-' && a.find_first_not_of("0123456789") != std::string::npos) data_file = a;
     else if (ndims < 3 && a[0] != '-') dims[ndims++] = std::atoi(argv[i]);
     else ndims = -1000;
   }
-  if (ndims != 3) {
+  if (!(ndims == 3 && data_file.empty()) && !(ndims == 0 && !data_file.empty())) {
     if (rank == 0)
     cerr << "Usage:" << endl
          << "Mode 1: " << argv[0] << " nx ny nz [--iters N] [--stencil 27|7] [--tolerance T] [--device-only] [--check] [--ranks N]" << endl
          << "     where nx, ny and nz are the local sub-block dimensions." << endl
-         << "Mode 2 (HPC_data_file) of the reference is deprecated upstream and not supported." << endl;
+         << "Mode 2: " << argv[0] << " HPC_data_file [same options]" << endl
+         << "     where HPC_data_file is a globally accessible file containing matrix data." << endl;
     return 1;
   }
-  const int nx = dims[0], ny = dims[1], nz = dims[2];
-  const long long n = (long long)nx * ny * nz;
+  int nx = dims[0], ny = dims[1], nz = dims[2];
+  long long n = (long long)nx * ny * nz;
   if (27 * n > 2147483647LL) device_only = 1;
+  if (!data_file.empty()) device_only = 0;
   (void)argc;
   if (hpccg_api_set_options(stencil, device_only ? 0 : 1)) {
     cerr << hpccg_last_error() << endl;
@@ -181,7 +187,14 @@ static int run_rank(int argc, char *argv[], FileWorld *world) {
     }
   }
 
-  generate_matrix(nx, ny, nz, &A, &x, &b, &xexact);
+  if (data_file.empty()) {
+    generate_matrix(nx, ny, nz, &A, &x, &b, &xexact);
+  } else {
+    read_HPC_row(const_cast<char *>(data_file.c_str()), &A, &x, &b, &xexact);  // main.cpp:160-167
+    nx = A->total_nrow;
+    ny = nz = 1;
+    n = A->local_nrow;
+  }
   if (world) {
     const double t6 = mytimer();
     make_local_matrix(A);  // main.cpp:179-180

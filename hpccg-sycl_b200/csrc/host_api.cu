@@ -450,6 +450,124 @@ void generate_matrix(int nx, int ny, int nz, HPC_Sparse_Matrix **A, double **x, 
 }
 
 // ====================================================================================================
+// read_HPC_row (read_HPC_row.cpp:217-373)
+// ====================================================================================================
+static int read_HPC_row_impl(const char *data_file, HPC_Sparse_Matrix **Aout, double **x, double **b, double **xexact) {
+  if (!data_file || !Aout || !x || !b || !xexact) return fail(HPCCG_ERR_ARG, "read_HPC_row: bad argument");
+  FILE *in = std::fopen(data_file, "r");
+  if (!in) return fail(HPCCG_ERR_ARG, "read_HPC_row: cannot open file: %s", data_file);
+  struct Closer {
+    FILE *f;
+    ~Closer() { std::fclose(f); }
+  } closer{in};
+  int total_nrow = 0;
+  long long total_nnz = 0;
+  if (std::fscanf(in, "%d", &total_nrow) != 1 || std::fscanf(in, "%lld", &total_nnz) != 1 || total_nrow <= 0)
+    return fail(HPCCG_ERR_ARG, "read_HPC_row: bad header in %s", data_file);
+  const RankContext &c = ctx();
+  const int size = c.size, rank = c.rank;
+  // the reference's row distribution, off-by-rank quirk included (read_HPC_row.cpp:257-267)
+  const int chunksize = total_nrow / size, remainder = total_nrow % size;
+  int mp = chunksize;
+  if (rank < remainder) mp++;
+  const int local_nrow = mp;
+  int off = rank * (chunksize + 1);
+  if (rank > remainder) off -= (rank - remainder);
+  const int start_row = off, stop_row = off + mp - 1;
+  if (local_nrow <= 0) return fail(HPCCG_ERR_ARG, "read_HPC_row: rank %d of %d gets no row of the %d", rank, size, total_nrow);
+
+  HPC_Sparse_Matrix *A = new HPC_Sparse_Matrix();
+  std::memset(A, 0, sizeof *A);
+  A->nnz_in_row = new int[local_nrow];
+  A->ptr_to_vals_in_row = new double *[local_nrow];
+  A->ptr_to_inds_in_row = new int *[local_nrow];
+  A->ptr_to_diags = new double *[local_nrow];
+  *x = new_vector(local_nrow, true);
+  *b = new_vector(local_nrow, true);
+  *xexact = new_vector(local_nrow, true);
+  auto bail = [&](const char *what) {
+    HPC_Sparse_Matrix *p = A;
+    destroyMatrix(p);
+    free_vectors(*x, *b, *xexact);
+    *x = *b = *xexact = nullptr;
+    return fail(HPCCG_ERR_ARG, "read_HPC_row: %s in %s", what, data_file);
+  };
+  long long local_nnz = 0;
+  int cur = 0, l = 0;
+  for (int i = 0; i < total_nrow; ++i) {
+    if (std::fscanf(in, "%d", &l) != 1 || l < 0) return bail("bad row length");
+    if (start_row <= i && i <= stop_row) {
+      local_nnz += l;
+      A->nnz_in_row[cur++] = l;
+    }
+  }
+  if (local_nnz > INT_MAX) return bail("more than 2^31 local entries");
+  A->list_of_vals = new double[std::max<long long>(local_nnz, 1)];
+  A->list_of_inds = new int[std::max<long long>(local_nnz, 1)];
+  A->ptr_to_vals_in_row[0] = A->list_of_vals;
+  A->ptr_to_inds_in_row[0] = A->list_of_inds;
+  for (int i = 1; i < local_nrow; ++i) {
+    A->ptr_to_vals_in_row[i] = A->ptr_to_vals_in_row[i - 1] + A->nnz_in_row[i - 1];
+    A->ptr_to_inds_in_row[i] = A->ptr_to_inds_in_row[i - 1] + A->nnz_in_row[i - 1];
+  }
+  cur = 0;
+  double v = 0.0;
+  for (int i = 0; i < total_nrow; ++i) {
+    int cur_nnz = 0;
+    if (std::fscanf(in, "%d", &cur_nnz) != 1) return bail("bad row record");
+    const bool mine = start_row <= i && i <= stop_row;
+    if (mine && cur_nnz != A->nnz_in_row[cur]) return bail("row length differs from the length table");
+    for (int j = 0; j < cur_nnz; ++j) {
+      if (std::fscanf(in, "%lf %d", &v, &l) != 2) return bail("bad entry");
+      if (mine) {
+        if (l < 0 || l >= total_nrow) return bail("column id outside the matrix");
+        A->ptr_to_vals_in_row[cur][j] = v;
+        A->ptr_to_inds_in_row[cur][j] = l;
+      }
+    }
+    if (mine) {
+      // the reference leaves ptr_to_diags unset here (read_HPC_row.cpp:244,369); point it at the diagonal where there is one
+      A->ptr_to_diags[cur] = A->ptr_to_vals_in_row[cur];
+      for (int j = 0; j < cur_nnz; ++j)
+        if (A->ptr_to_inds_in_row[cur][j] == i) A->ptr_to_diags[cur] = A->ptr_to_vals_in_row[cur] + j;
+      ++cur;
+    }
+  }
+  cur = 0;
+  double xt, bt, xxt;
+  for (int i = 0; i < total_nrow; ++i) {
+    if (std::fscanf(in, "%lf %lf %lf", &xt, &bt, &xxt) != 3) return bail("bad vector record");
+    if (start_row <= i && i <= stop_row) {
+      (*x)[cur] = xt;
+      (*b)[cur] = bt;
+      (*xexact)[cur] = xxt;
+      ++cur;
+    }
+  }
+  A->start_row = start_row;
+  A->stop_row = stop_row;
+  A->total_nrow = total_nrow;
+  A->total_nnz = total_nnz;
+  A->local_nrow = local_nrow;
+  A->local_ncol = local_nrow;
+  A->local_nnz = (int)local_nnz;
+  A->rank = rank;
+  A->size = size;
+  A->host_rows = 1;
+  A->gen_stencil = 0;
+  *Aout = A;
+  return 0;
+}
+
+void read_HPC_row(char *data_file, HPC_Sparse_Matrix **A, double **x, double **b, double **xexact) {
+  std::printf("Reading matrix info from %s...\n", data_file);  // read_HPC_row.cpp:235
+  if (read_HPC_row_impl(data_file, A, x, b, xexact)) {
+    std::printf("Error: %s\n", hpccg_last_error());
+    std::exit(1);  // the reference exits on an unreadable file (:239-243)
+  }
+}
+
+// ====================================================================================================
 // make_local_matrix (make_local_matrix.cpp:58-610)
 // ====================================================================================================
 static int make_local_matrix_impl(HPC_Sparse_Matrix *A) {
@@ -780,6 +898,10 @@ int hpccg_api_set_print(int on) {
 
 int hpccg_api_generate_matrix(int nx, int ny, int nz, void **A, double **x, double **b, double **xexact) {
   return generate_matrix_impl(nx, ny, nz, reinterpret_cast<HPC_Sparse_Matrix **>(A), x, b, xexact);
+}
+
+int hpccg_api_read_HPC_row(const char *data_file, void **A, double **x, double **b, double **xexact) {
+  return read_HPC_row_impl(data_file, reinterpret_cast<HPC_Sparse_Matrix **>(A), x, b, xexact);
 }
 
 int hpccg_api_make_local_matrix(void *A) { return make_local_matrix_impl(static_cast<HPC_Sparse_Matrix *>(A)); }

@@ -12,6 +12,11 @@
 // thread's rank context (hpccg_ctx_set / hpccg_api_set_options).
 void generate_matrix(int nx, int ny, int nz, HPC_Sparse_Matrix **A, double **x, double **b, double **xexact);
 
+// read_HPC_row.hpp:56-57 -- the reference's (deprecated, README.md:114-118) matrix-file input: header `total_nrow
+// total_nnz`, the row lengths, then per row `nnz (value column)*`, then per row `x b xexact`.  Rows are dealt to the ranks
+// in contiguous chunks exactly as read_HPC_row.cpp:257-267; column ids stay global until make_local_matrix.
+void read_HPC_row(char *data_file, HPC_Sparse_Matrix **A, double **x, double **b, double **xexact);
+
 // make_local_matrix.hpp:48 -- global -> local column ids, externals numbered per owner in
 // first-encounter order, send lists negotiated through the context's set-up collective.
 void make_local_matrix(HPC_Sparse_Matrix *A);

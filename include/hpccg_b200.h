@@ -181,6 +181,9 @@ int hpccg_api_set_print(int on);
 int hpccg_api_set_matrix_format(int format);
 /* generate_matrix.hpp:58 */
 int hpccg_api_generate_matrix(int nx, int ny, int nz, void **A, double **x, double **b, double **xexact);
+/* read_HPC_row.hpp:56-57 -- matrix-file input (deprecated upstream, README.md:114-118); rows dealt to the ranks as
+ * read_HPC_row.cpp:257-267.  Returns non-zero (file unreadable / malformed) where the reference exit()s. */
+int hpccg_api_read_HPC_row(const char *data_file, void **A, double **x, double **b, double **xexact);
 /* make_local_matrix.hpp:48 */
 int hpccg_api_make_local_matrix(void *A);
 /* HPCCG.hpp:61-63 */

@@ -40,7 +40,7 @@ if [ ! -f "$REF/HPCCG.cpp" ]; then
   exit 0
 fi
 
-COMMON_TUS="generate_matrix mytimer HPC_sparsemv HPCCG waxpby ddot compute_residual HPC_Sparse_Matrix YAML_Doc YAML_Element"
+COMMON_TUS="generate_matrix mytimer HPC_sparsemv HPCCG waxpby ddot compute_residual HPC_Sparse_Matrix YAML_Doc YAML_Element read_HPC_row"
 MPI_TUS="make_local_matrix exchange_externals"
 SED_NONE='s/^$//'
 SED_MAXEXT='s/max_external = 100000/max_external = 2200000/'

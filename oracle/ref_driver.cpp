@@ -39,6 +39,7 @@
 #include "ddot.hpp"
 #include "generate_matrix.hpp"
 #include "mytimer.hpp"
+#include "read_HPC_row.hpp"
 #include "waxpby.hpp"
 #ifdef USING_MPI
 #include "exchange_externals.hpp"
@@ -64,6 +65,7 @@ struct RefRank {
 struct RefWorld {
   int nx, ny, nz, size, stencil7;
   std::vector<RefRank> ranks;
+  std::string file;  // non-empty: matrix read by the reference's read_HPC_row (read_HPC_row.cpp:217-373)
 };
 
 void run_ranks(int size, void (*fn)(int, void *), void *arg) {
@@ -78,7 +80,13 @@ void run_ranks(int size, void (*fn)(int, void *), void *arg) {
 void gen_rank(int rank, void *arg) {
   RefWorld *w = static_cast<RefWorld *>(arg);
   RefRank &rr = w->ranks[rank];
-  if (w->stencil7) generate_matrix_7pt(w->nx, w->ny, w->nz, &rr.A, &rr.x, &rr.b, &rr.xexact);
+  if (!w->file.empty()) {
+    read_HPC_row(const_cast<char *>(w->file.c_str()), &rr.A, &rr.x, &rr.b, &rr.xexact);
+    // read_HPC_row.cpp never stores the two list pointers in the struct (:356-370); they are the first row's pointers
+    rr.A->list_of_vals = rr.A->ptr_to_vals_in_row[0];
+    rr.A->list_of_inds = rr.A->ptr_to_inds_in_row[0];
+    for (int i = 0; i < rr.A->local_nrow; ++i) rr.A->ptr_to_diags[i] = rr.A->list_of_vals;  // left uninitialised there
+  } else if (w->stencil7) generate_matrix_7pt(w->nx, w->ny, w->nz, &rr.A, &rr.x, &rr.b, &rr.xexact);
   else generate_matrix(w->nx, w->ny, w->nz, &rr.A, &rr.x, &rr.b, &rr.xexact);
   long long s = 0;
   for (int i = 0; i < rr.A->local_nrow; ++i) s += rr.A->nnz_in_row[i];
@@ -115,7 +123,16 @@ void *ref_create(int nx, int ny, int nz, int size, int stencil7) {
 #ifndef USING_MPI
   if (size != 1) return nullptr;
 #endif
-  RefWorld *w = new RefWorld{nx, ny, nz, size, stencil7, std::vector<RefRank>(size)};
+  RefWorld *w = new RefWorld{nx, ny, nz, size, stencil7, std::vector<RefRank>(size), std::string()};
+  run_ranks(size, gen_rank, w);
+  return w;
+}
+
+void *ref_create_from_file(const char *path, int size) {
+#ifndef USING_MPI
+  if (size != 1) return nullptr;
+#endif
+  RefWorld *w = new RefWorld{0, 0, 0, size, 0, std::vector<RefRank>(size), std::string(path)};
   run_ranks(size, gen_rank, w);
   return w;
 }

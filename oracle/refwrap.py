@@ -66,6 +66,8 @@ def _lib(variant: str):
     lib.ref_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _PD, C.POINTER(C.c_int), _PD, _PD, _PPD]
     lib.ref_compute_residual.argtypes = [C.c_void_p, _PPD, _PD]
     if variant != "oracle":
+        lib.ref_create_from_file.restype = C.c_void_p
+        lib.ref_create_from_file.argtypes = [C.c_char_p, C.c_int]
         lib.ref_yaml_report.argtypes = [C.c_int] * 4 + [C.c_double, _PD, C.c_double, C.c_double, C.c_int, C.c_int,
                                                         _PD, C.c_char_p, C.c_int]
     _libs[variant] = lib
@@ -106,6 +108,19 @@ class RefWorld:
         self.h = self.lib.ref_create(nx, ny, nz, size, 1 if stencil == 7 else 0)
         if not self.h:
             raise RuntimeError(f"ref_create failed (variant {variant}, size {size})")
+
+    @classmethod
+    def from_file(cls, path: str, size: int = 1, variant: str | None = None):
+        """The reference's read_HPC_row (read_HPC_row.cpp:217-373) on `size` ranks (+ make_local_matrix when size > 1)."""
+        self = cls.__new__(cls)
+        self.variant = variant or ("mpi" if size > 1 else "serial")
+        self.lib = _lib(self.variant)
+        self.size = size
+        self.dims = None
+        self.h = self.lib.ref_create_from_file(str(path).encode(), size)
+        if not self.h:
+            raise RuntimeError("ref_create_from_file failed")
+        return self
 
     def close(self):
         if self.h:

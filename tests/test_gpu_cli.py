@@ -59,3 +59,16 @@ def test_cli_ranks_mode(H, cuda, tmp_path):
     assert out.count("Initial Residual = ") == 2  # rank 0 only, once per solve (the driver solves twice)
     m = re.search(r"Difference between computed and exact: (\S+)", out)
     assert m and float(m.group(1)) <= 1e-12
+
+
+def test_cli_mode2_matrix_file(H, refwrap, cuda, tmp_path):
+    """`test_HPCCG HPC_data_file` (main.cpp:160-167): the reference's 10x10x10 matrix written in read_HPC_row's format gives
+    the same residual lines as the generated one (out.txt:1-2)."""
+    from test_read_hpc_row import stencil_file
+    path, _ = stencil_file(refwrap, tmp_path, dims=(10, 10, 10))
+    res = run([str(path), "--check"], tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert f"Reading matrix info from {path}..." in res.stdout
+    assert "Initial Residual = 258.24\n" in res.stdout and "Iteration = 15   Residual = 2.15402e-06\n" in res.stdout
+    assert "Number of iterations: 149\n" in res.stdout
+    assert run([str(tmp_path / "nope.dat")], tmp_path).returncode == 1

@@ -1,0 +1,131 @@
+"""read_HPC_row (read_HPC_row.cpp:217-373): the reference's matrix-file input.  The reference ships no data
+file, so the tests write files in the format its reader expects -- from the reference's own generated matrix and from a
+random diagonally dominant matrix with ragged rows -- and compare this library's reader with the REFERENCE's reader on the
+same file: every array bit for bit, for 1, 2 and 3 ranks (row dealing of read_HPC_row.cpp:257-267 + make_local_matrix)."""
+import numpy as np
+import pytest
+
+from conftest import ref_variant
+
+
+def write_hpc_file(path, nnz, vals, cols, x, b, xexact):
+    n = len(nnz)
+    with open(path, "w") as f:
+        f.write(f"{n} {int(nnz.sum())}\n")
+        f.write(" ".join(str(int(c)) for c in nnz) + "\n")
+        k = 0
+        for i in range(n):
+            row = [str(int(nnz[i]))]
+            for j in range(nnz[i]):
+                row.append(repr(float(vals[k + j])))
+                row.append(str(int(cols[k + j])))
+            k += nnz[i]
+            f.write(" ".join(row) + "\n")
+        for i in range(n):
+            f.write(f"{float(x[i])!r} {float(b[i])!r} {float(xexact[i])!r}\n")
+
+
+def stencil_file(refwrap, tmp_path, dims=(7, 5, 3)):
+    with refwrap.RefWorld(*dims, variant="oracle") as R:
+        args = [R.array(0, a) for a in ("nnz_in_row", "list_of_vals", "list_of_inds", "x", "b", "xexact")]
+    path = tmp_path / "stencil.dat"
+    write_hpc_file(path, *args)
+    return path, args
+
+
+def random_file(tmp_path, n=157, seed=4):
+    rng = np.random.default_rng(seed)
+    nnz, vals, cols = [], [], []
+    for i in range(n):
+        k = int(rng.integers(1, 12))
+        c = sorted(set(rng.integers(0, n, k).tolist()) | {i})
+        v = rng.uniform(-1, 1, len(c))
+        v[c.index(i)] = 20.0 + rng.uniform(0, 1)  # diagonally dominant
+        nnz.append(len(c)); vals += v.tolist(); cols += c
+    nnz = np.array(nnz, dtype=np.int32); vals = np.array(vals); cols = np.array(cols, dtype=np.int32)
+    xexact = rng.uniform(-1, 1, n)
+    b = np.zeros(n); k = 0
+    for i in range(n):
+        s = 0.0
+        for j in range(nnz[i]):
+            s += vals[k + j] * xexact[cols[k + j]]
+        b[i] = s; k += nnz[i]
+    path = tmp_path / "random.dat"
+    write_hpc_file(path, nnz, vals, cols, np.zeros(n), b, xexact)
+    return path, (nnz, vals, cols, np.zeros(n), b, xexact)
+
+
+ARRAYS = ["nnz_in_row", "list_of_inds", "list_of_vals", "ind_offsets", "val_offsets"]
+HALO = ["external_index", "external_local_index", "elements_to_send", "neighbors", "recv_length", "send_length"]
+SCALARS = ["start_row", "stop_row", "total_nrow", "total_nnz", "local_nrow", "local_ncol", "local_nnz", "nnz_sum",
+           "num_external", "num_send_neighbors", "total_to_be_sent"]
+
+
+@pytest.mark.parametrize("kind", ["stencil", "random"])
+@pytest.mark.parametrize("size", [1, 2, 3])
+def test_reader_matches_reference_reader(H, refwrap, tmp_path, kind, size):
+    variant = "mpi" if size > 1 else "serial"
+    if not refwrap.available(variant):
+        pytest.skip("the reference build (oracle/_ref) is needed: the C restatement has no file reader")
+    path, _ = stencil_file(refwrap, tmp_path) if kind == "stencil" else random_file(tmp_path)
+
+    def body(r):
+        A = H.read_HPC_row(path)
+        if size > 1:
+            H.make_local_matrix(A)
+        return A
+    if size == 1:
+        H.set_rank(0, 1)
+        mats = [body(0)]
+    else:
+        mats = H.run_local_world(size, body)
+    R = refwrap.RefWorld.from_file(path, size=size, variant=variant)
+    try:
+        for r, A in enumerate(mats):
+            for s in SCALARS:
+                assert A.scalar(s) == R.scalar(r, s), (r, s)
+            for a in ARRAYS + (HALO if size > 1 else []):
+                assert np.array_equal(A.array(a), R.array(r, a)), (r, a)
+            for v, name in ((A.x, "x"), (A.b, "b"), (A.xexact, "xexact")):
+                assert np.array_equal(v, R.array(r, name)), (r, name)
+    finally:
+        R.close()
+        for A in mats:
+            A.destroy()
+
+
+def test_reader_errors_are_reported(H, tmp_path):
+    H.set_rank(0, 1)
+    with pytest.raises(H.HpccgError, match="cannot open"):
+        H.read_HPC_row(tmp_path / "missing.dat")
+    bad = tmp_path / "bad.dat"
+    bad.write_text("3 3\n1 1 1\n1 1.0 0\n1 1.0 7\n1 1.0 2\n0 0 0\n0 0 0\n0 0 0\n")
+    with pytest.raises(H.HpccgError, match="column id"):
+        H.read_HPC_row(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["stencil", "random"])
+def test_file_matrix_on_the_gpu(H, refwrap, cuda, tmp_path, kind):
+    """SpMV bit-exact and CG history within the bar on a matrix that came from a file (ragged rows -> run-time slot count)."""
+    from test_gpu_solve import check_history
+    if not refwrap.available("serial"):
+        pytest.skip("needs oracle/_ref")
+    path, (nnz, vals, cols, x0, b, xexact) = stencil_file(refwrap, tmp_path) if kind == "stencil" else random_file(tmp_path)
+    H.set_rank(0, 1)
+    A = H.read_HPC_row(path)
+    n = A.local_nrow
+    R = refwrap.RefWorld.from_file(path)
+    try:
+        v = np.random.default_rng(8).uniform(-1, 1, n)
+        y = np.empty(n)
+        H.HPC_sparsemv(A, v, y)
+        assert np.array_equal(y, R.spmv([v.copy()])[0])
+        ref = R.solve(60)
+        x = A.x.copy()
+        niters, normr, _, hist = H.HPCCG(A, A.b, x, 60, 0.0)
+        check_history(hist, ref["hist"], niters, ref["niters"])
+        assert np.abs(x - A.xexact).max() <= 1e-10
+    finally:
+        R.close()
+        A.destroy()
