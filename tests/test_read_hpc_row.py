@@ -34,14 +34,20 @@ def stencil_file(refwrap, tmp_path, dims=(7, 5, 3)):
 
 
 def random_file(tmp_path, n=157, seed=4):
+    """A random SYMMETRIC, diagonally dominant (hence SPD) matrix with ragged rows, columns sorted within a row."""
     rng = np.random.default_rng(seed)
+    rows = [dict() for _ in range(n)]
+    for i in range(n):
+        for j in rng.integers(0, n, int(rng.integers(0, 6))).tolist():
+            if j != i:
+                v = float(rng.uniform(-1, 1))
+                rows[i][j] = v
+                rows[j][i] = v
     nnz, vals, cols = [], [], []
     for i in range(n):
-        k = int(rng.integers(1, 12))
-        c = sorted(set(rng.integers(0, n, k).tolist()) | {i})
-        v = rng.uniform(-1, 1, len(c))
-        v[c.index(i)] = 20.0 + rng.uniform(0, 1)  # diagonally dominant
-        nnz.append(len(c)); vals += v.tolist(); cols += c
+        rows[i][i] = sum(abs(v) for v in rows[i].values()) + 1.0 + float(rng.uniform(0, 1))
+        c = sorted(rows[i])
+        nnz.append(len(c)); cols += c; vals += [rows[i][j] for j in c]
     nnz = np.array(nnz, dtype=np.int32); vals = np.array(vals); cols = np.array(cols, dtype=np.int32)
     xexact = rng.uniform(-1, 1, n)
     b = np.zeros(n); k = 0
