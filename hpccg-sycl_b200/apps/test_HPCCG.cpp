@@ -244,49 +244,43 @@ static int run_rank(int argc, char *argv[], FileWorld *world) {
     return ierr ? 2 : 0;
   }
 
+  // Report tree with the reference's keys (main.cpp:230-298), built from tables.
   YAML_Doc doc("hpccg", "1.0");
-  doc.add("Parallelism", "");
-  if (world) doc.get("Parallelism")->add("Number of MPI ranks", size);  // ranks are GPU processes here
-  else doc.get("Parallelism")->add("MPI not enabled", "");
-  doc.get("Parallelism")->add("OpenMP not enabled", "");
-  doc.get("Parallelism")->add("SYCL not enabled", "");
-  doc.get("Parallelism")->add("Number of B200 GPUs", size);
-  doc.add("Dimensions", "");
-  doc.get("Dimensions")->add("nx", nx);
-  doc.get("Dimensions")->add("ny", ny);
-  doc.get("Dimensions")->add("nz", nz);
+  YAML_Element *par = doc.add("Parallelism", "");
+  if (world) par->add("Number of MPI ranks", size);  // ranks are GPU processes here
+  else par->add("MPI not enabled", "");
+  par->add("OpenMP not enabled", "");
+  par->add("SYCL not enabled", "");
+  par->add("Number of B200 GPUs", size);
+  YAML_Element *dim = doc.add("Dimensions", "");
+  const char *axes[3] = {"nx", "ny", "nz"};
+  const int extent[3] = {nx, ny, nz};
+  for (int i = 0; i < 3; ++i) dim->add(axes[i], extent[i]);
   doc.add("Number of iterations", niters);
   doc.add("Final residual", normr);
   doc.add("#********** Performance Summary (times in sec) ***********", "");
-  doc.add("Time Summary", "");
-  doc.get("Time Summary")->add("Total   ", t[0]);
-  doc.get("Time Summary")->add("DDOT    ", t[1]);
-  doc.get("Time Summary")->add("WAXPBY  ", t[2]);
-  doc.get("Time Summary")->add("SPARSEMV", t[3]);
-  doc.add("FLOPS Summary", "");
-  doc.get("FLOPS Summary")->add("Total   ", fnops);
-  doc.get("FLOPS Summary")->add("DDOT    ", fnops_ddot);
-  doc.get("FLOPS Summary")->add("WAXPBY  ", fnops_waxpby);
-  doc.get("FLOPS Summary")->add("SPARSEMV", fnops_sparsemv);
-  doc.add("MFLOPS Summary", "");
-  doc.get("MFLOPS Summary")->add("Total   ", fnops / t[0] / 1.0E6);
-  doc.get("MFLOPS Summary")->add("DDOT    ", fnops_ddot / t[1] / 1.0E6);
-  doc.get("MFLOPS Summary")->add("WAXPBY  ", fnops_waxpby / t[2] / 1.0E6);
-  doc.get("MFLOPS Summary")->add("SPARSEMV", fnops_sparsemv / (t[3]) / 1.0E6);
-  if (world) {  // main.cpp:284-298
-    doc.add("DDOT Timing Variations", "");
-    doc.get("DDOT Timing Variations")->add("Min DDOT MPI_Allreduce time", t4stats[0]);
-    doc.get("DDOT Timing Variations")->add("Max DDOT MPI_Allreduce time", t4stats[1]);
-    doc.get("DDOT Timing Variations")->add("Avg DDOT MPI_Allreduce time", t4stats[2]);
-    const double totalSparseMVTime = t[3] + t[5] + t[6];
-    doc.add("SPARSEMV OVERHEADS", "");
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV MFLOPS W OVERHEAD", fnops_sparsemv / (totalSparseMVTime) / 1.0E6);
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Time", (t[5] + t[6]));
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Pct", (t[5] + t[6]) / totalSparseMVTime * 100.0);
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Setup Time", (t[6]));
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Setup Pct", (t[6]) / totalSparseMVTime * 100.0);
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Time", (t[5]));
-    doc.get("SPARSEMV OVERHEADS")->add("SPARSEMV PARALLEL OVERHEAD Bdry Exch Pct", (t[5]) / totalSparseMVTime * 100.0);
+  const char *kernels[4] = {"Total   ", "DDOT    ", "WAXPBY  ", "SPARSEMV"};  // trailing blanks as in main.cpp:267-270
+  const double flop_count[4] = {fnops, fnops_ddot, fnops_waxpby, fnops_sparsemv};
+  YAML_Element *sum_t = doc.add("Time Summary", ""), *sum_f = doc.add("FLOPS Summary", ""), *sum_m = doc.add("MFLOPS Summary", "");
+  for (int i = 0; i < 4; ++i) {
+    sum_t->add(kernels[i], t[i]);
+    sum_f->add(kernels[i], flop_count[i]);
+    sum_m->add(kernels[i], flop_count[i] / t[i] / 1.0E6);
+  }
+  if (world) {  // the two blocks the reference prints under MPI only (main.cpp:284-298)
+    YAML_Element *var = doc.add("DDOT Timing Variations", "");
+    const char *stat[3] = {"Min", "Max", "Avg"};
+    for (int i = 0; i < 3; ++i) var->add(std::string(stat[i]) + " DDOT MPI_Allreduce time", t4stats[i]);
+    const double with_overhead = t[3] + t[5] + t[6];
+    const std::string head = "SPARSEMV PARALLEL OVERHEAD ";
+    YAML_Element *ov = doc.add("SPARSEMV OVERHEADS", "");
+    ov->add("SPARSEMV MFLOPS W OVERHEAD", fnops_sparsemv / with_overhead / 1.0E6);
+    const char *part[3] = {"", "Setup ", "Bdry Exch "};
+    const double part_s[3] = {t[5] + t[6], t[6], t[5]};
+    for (int i = 0; i < 3; ++i) {
+      ov->add(head + part[i] + "Time", part_s[i]);
+      ov->add(head + part[i] + "Pct", part_s[i] / with_overhead * 100.0);
+    }
   }
   // B200 block: the kernel times above are CUDA-event sums, fused kernels split by algorithmic bytes
   const double kernel_s = t[1] + t[2] + t[3];
