@@ -55,12 +55,15 @@ WORKLOADS = {
 }
 
 
-def bytes_per_row_iter(stencil: int, fmt: str = "sell") -> dict:
+def bytes_per_row_iter(stencil: int, fmt: str = "sell", eager_x: bool = False) -> dict:
     """Algorithmic HBM bytes per local row per CG iteration (SURVEY.md 8d / DESIGN.md): matrix streamed once
     (8 B value + 4 B column id per slot; one 2-byte pattern id per row in the opt-in pattern format), p gathered once, Ap written;
     x,p,r,Ap read + x,r written; r,p read + p written."""
     spmv = (2 if fmt == "pattern" else stencil * 12) + 16
-    return {"spmv_dot": spmv, "update_xr_dot": 48, "p_update": 24, "iteration": spmv + 72}
+    if eager_x:  # x += alpha p in the kernel after the SpMV: read x,p,r,Ap + write x,r ; then read r,p + write p
+        return {"spmv_dot": spmv, "update_xr_dot": 48, "p_update": 24, "iteration": spmv + 72}
+    # default: the x update rides in the next p-update: read r,Ap + write r ; then read x,r,p + write x,p
+    return {"spmv_dot": spmv, "update_xr_dot": 24, "p_update": 40, "iteration": spmv + 64}
 
 
 def parse_args():
@@ -79,6 +82,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: halo exchange not overlapped (A/B)")
     ap.add_argument("--unfused", action="store_true", help="literal reference kernel sequence (A/B)")
+    ap.add_argument("--eager-x", action="store_true", help="x += alpha p right after the SpMV instead of deferred into the p-update (A/B)")
     ap.add_argument("--format", default=os.environ.get("HPCCG_BENCH_FORMAT", "sell"), choices=["sell", "pattern"],
                     help="device-mirror format: sell = SELL-128 values + int32 columns (north-star layout, default); "
                          "pattern = lossless 16-bit row-pattern ids (SURVEY.md 8 f3)")
@@ -303,7 +307,9 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
             flags |= 2
         if args.unfused:
             flags |= 1
-        bpr = bytes_per_row_iter(stencil, fmt)
+        if args.eager_x:
+            flags |= 32
+        bpr = bytes_per_row_iter(stencil, fmt, args.eager_x or args.unfused)
 
         def step(acc=None):
             x.zero_()
@@ -446,7 +452,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
             "what": "same workload with the opt-in pattern-coded mirror (hpccg_dev_matrix_compress): one 16-bit pattern id per "
                     "row instead of 12 B per stored entry; bit-identical SpMV; its SpMV is bound by L1 gather throughput, not HBM",
             "value": also_pattern["value"], "unit": UNIT, "ms_per_step": also_pattern["ms_per_step"], "e2e": also_pattern.get("e2e"),
-            "bytes_per_row_iteration": bytes_per_row_iter(w["stencil"], "pattern")["iteration"],
+            "bytes_per_row_iteration": bytes_per_row_iter(w["stencil"], "pattern", args.eager_x or args.unfused)["iteration"],
             "mirror_bytes": also_pattern["ell_bytes"], "patterns": also_pattern["format"]["patterns"],
             "kernels": kp, "loop_frac_of_peak": kp["iteration"]["gbs"] / peak,
             "check": {"niters": also_pattern["niters"], "normr": also_pattern["normr"], "x_max_err": also_pattern["x_max_err"]}}
@@ -464,7 +470,7 @@ def main():
         raise SystemExit("for N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
     w = resolve_workload(args, size)
-    bpr = bytes_per_row_iter(w["stencil"], args.format)
+    bpr = bytes_per_row_iter(w["stencil"], args.format, args.eager_x or args.unfused)
     config = {"workload": f"{w['name']}: {w['stencil']}-pt stencil, local {w['nx']}x{w['ny']}x{w['nz']} per GPU, "
                           f"global {w['nx']}x{w['ny']}x{w['nz'] * size}, max_iter {args.max_iter} ({args.max_iter - 1} CG iterations per step)",
               "nx": w["nx"], "ny": w["ny"], "nz_local": w["nz"], "stencil": w["stencil"], "max_iter": args.max_iter,

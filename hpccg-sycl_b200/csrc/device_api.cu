@@ -1112,6 +1112,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   const int L = (int)rk.size();
   const bool multi = R > 1;
   const bool unfused = (flags & HPCCG_SOLVE_UNFUSED) != 0;
+  const bool defer_x = !unfused && !(flags & HPCCG_SOLVE_EAGER_X);  // x += alpha p rides in the next p-update (kernels.cuh)
   bool overlap = nccl && !(flags & HPCCG_SOLVE_NO_OVERLAP) && !unfused;
   if (max_iter < 1) max_iter = 1;
   for (auto &q : rk) {
@@ -1275,8 +1276,15 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     timers.tick(T_PUPD);
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
-      if (k == 1) HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
-      else HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, &m->state->beta, m->p, m->p, m->state, s));
+      if (k == 1) {
+        HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
+      } else if (defer_x) {
+        p_update_x_kernel<<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
+        count_launch();
+        HPCCG_LAUNCH_CHECK();
+      } else {
+        HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, &m->state->beta, m->p, m->p, m->state, s));
+      }
     }
     timers.tock();
 
@@ -1328,8 +1336,12 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       for (int q = 0; q < L; ++q) {
         hpccg_dev_matrix *m = rk[q].m;
         const int grid = stream_grid((m->n + 1) / 2);
-        update_xr_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->p, m->Ap, rk[q].x, m->r, m->partials, grid,
-                                                        &m->state->counter, fp_for(FIN_RR, q, k, last, true));
+        if (defer_x)
+          update_r_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
+                                                         fp_for(FIN_RR, q, k, last, true));
+        else
+          update_xr_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->p, m->Ap, rk[q].x, m->r, m->partials, grid,
+                                                          &m->state->counter, fp_for(FIN_RR, q, k, last, true));
         count_launch();
       }
       HPCCG_LAUNCH_CHECK();
@@ -1350,6 +1362,14 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       HPCCG_CUDA(cudaStreamSynchronize(s));
       if (*h_active == 0) break;
     }
+  }
+  if (defer_x && max_iter > 1) {  // the x update of the last executed iteration
+    for (int q = 0; q < L; ++q) {
+      hpccg_dev_matrix *m = rk[q].m;
+      x_fixup_kernel<<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->p, rk[q].x);
+      count_launch();
+    }
+    HPCCG_LAUNCH_CHECK();
   }
   if (capture_only) return 0;
   HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
@@ -1374,8 +1394,10 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     timers.collect(acc, 16);
     // Fused kernels are split by the unfused algorithmic byte counts ("times[]"):
     //   SpMV+p.Ap : 340n SpMV / 16n ddot ; update+r.r : 48n waxpby / 8n ddot
-    times[1] = acc[T_DDOT] + acc[T_FUSED_SPMV] * (16.0 / 356.0) + acc[T_FUSED_UPD] * (8.0 / 56.0);
-    times[2] = acc[T_WAXPBY] + acc[T_FUSED_UPD] * (48.0 / 56.0);
+    //   deferred-x form: r-update+r.r : 24n waxpby / 8n ddot ; the p-update kernel carries both remaining waxpbys
+    const double upd_dot = defer_x ? 8.0 / 32.0 : 8.0 / 56.0;
+    times[1] = acc[T_DDOT] + acc[T_FUSED_SPMV] * (16.0 / 356.0) + acc[T_FUSED_UPD] * upd_dot;
+    times[2] = acc[T_WAXPBY] + acc[T_FUSED_UPD] * (1.0 - upd_dot);
     times[3] = acc[T_SPMV] + acc[T_FUSED_SPMV] * (340.0 / 356.0);
     times[2] += acc[T_PUPD];
     times[4] = acc[T_ALLRED] + t4_host;

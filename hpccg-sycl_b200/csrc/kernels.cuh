@@ -786,6 +786,82 @@ update_xr_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ 
   publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
 }
 
+// ---- the loop's two vector kernels with the x update deferred by one kernel -----------------------------------------
+// HPCCG.cpp:383 (x += alpha p) only needs p_k, which the NEXT p-update reads anyway, so it moves there: the kernel after the
+// SpMV updates r and reduces r.r (24 B/row), the p-update applies the previous iteration's x update and forms the new p
+// (40 B/row) -- 64 B/row instead of 48 + 24, every element still computed by the same two un-contracted operations.
+// The update of the last executed iteration is applied by x_fixup_kernel when the loop has ended.
+__global__ void __launch_bounds__(kThreads)
+update_r_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ Ap, double *__restrict__ r, double *partials,
+                    int total_partials, unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+  const double nalpha = -(*alpha_dev);
+  double acc = 0.0;
+  const int npair = n >> 1;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+    const long long e = 2 * (long long)i;
+    const double2 av = ld_stream_f64x2(Ap + e);
+    double2 rv = *reinterpret_cast<const double2 *>(r + e);
+    rv.x = __dadd_rn(rv.x, __dmul_rn(nalpha, av.x));
+    rv.y = __dadd_rn(rv.y, __dmul_rn(nalpha, av.y));
+    *reinterpret_cast<double2 *>(r + e) = rv;
+    acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
+    acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int i = n - 1;
+    const double rn = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
+    r[i] = rn;
+    acc = __dadd_rn(acc, __dmul_rn(rn, rn));
+  }
+  const double total = block_sum(acc, smem);
+  publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
+}
+
+// x += alpha_{k-1} p_{k-1} (deferred HPCCG.cpp:383) ; p_k = r + beta p_{k-1} (HPCCG.cpp:369).  alpha, beta from the device state.
+__global__ void __launch_bounds__(kThreads)
+p_update_x_kernel(int n, const CgState *st, const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x) {
+  if (st->active == 0) return;
+  const double alpha = st->alpha, beta = st->beta;
+  const int npair = n >> 1;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+    const long long e = 2 * (long long)i;
+    const double2 rv = ld_stream_f64x2(r + e);
+    double2 pv = *reinterpret_cast<const double2 *>(p + e);
+    double2 xv = *reinterpret_cast<const double2 *>(x + e);
+    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+    pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
+    pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
+    *reinterpret_cast<double2 *>(x + e) = xv;
+    *reinterpret_cast<double2 *>(p + e) = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int i = n - 1;
+    const double po = p[i];
+    x[i] = __dadd_rn(x[i], __dmul_rn(alpha, po));
+    p[i] = __dadd_rn(r[i], __dmul_rn(beta, po));
+  }
+}
+
+// After the loop: the x update of the last executed iteration (niters >= 1), HPCCG.cpp:383.
+__global__ void __launch_bounds__(kThreads)
+x_fixup_kernel(int n, const CgState *st, const double *__restrict__ p, double *__restrict__ x) {
+  if (st->niters < 1) return;
+  const double alpha = st->alpha;
+  const int npair = n >> 1;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
+    const long long e = 2 * (long long)i;
+    const double2 pv = ld_stream_f64x2(p + e);
+    double2 xv = *reinterpret_cast<const double2 *>(x + e);
+    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+    *reinterpret_cast<double2 *>(x + e) = xv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] = __dadd_rn(x[n - 1], __dmul_rn(alpha, p[n - 1]));
+}
+
 // ---- HPCCG.cpp:352-353 fused: r = b - Ap (waxpby alpha==1 branch, beta=-1) and r.r ------------------------
 __global__ void __launch_bounds__(kThreads)
 residual_dot_kernel(int n, const double *__restrict__ b, const double *__restrict__ Ap, double *__restrict__ r,
