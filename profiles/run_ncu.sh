@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
 echo "launch list rc=$?"
 # the top kernels, once per change: fused SpMV+dot, fused update+dot, p-update (skip the first solve's launches)
 ncu --set full --clock-control none --import-source on \
-    -k 'regex:spmv_sell_tma_kernel|spmv_ell_kernel|update_xr_dot_kernel|waxpby_kernel' -s 30 -c 6 -f -o gpurun_out/${TAG}_full \
+    -k 'regex:spmv_sell_tma_kernel|spmv_ell_kernel|update_r_dot_kernel|p_update_x_kernel|update_xr_dot_kernel' -s 30 -c 6 -f -o gpurun_out/${TAG}_full \
     $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -8
