@@ -284,7 +284,13 @@ static int tma_variant() {
 
 #define HPCCG_TMA_DISPATCH(FN, DOT, ...)                                   \
   do {                                                                     \
-    if (m->slots == 7) return FN<7, 2, 4, DOT>(__VA_ARGS__);               \
+    if (m->slots == 7) {                                                   \
+      switch (tma_variant()) {                                             \
+        case 1: return FN<7, 2, 8, DOT>(__VA_ARGS__);                      \
+        case 2: return FN<7, 4, 4, DOT>(__VA_ARGS__);                      \
+        default: return FN<7, 2, 4, DOT>(__VA_ARGS__);                     \
+      }                                                                    \
+    }                                                                      \
     switch (tma_variant()) {                                               \
       case 1: return FN<27, 1, 2, DOT>(__VA_ARGS__);                       \
       case 2: return FN<27, 1, 5, DOT>(__VA_ARGS__);                       \
