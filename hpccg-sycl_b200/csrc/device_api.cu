@@ -356,6 +356,16 @@ static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, co
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+static bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31) == 0; }
+// 256-bit accesses in the loop's vector kernels unless HPCCG_B200_VEC=2 (A/B) or a caller's vector is only 16-byte aligned
+static bool use_vec4(const void *a, const void *b, const void *c) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = std::getenv("HPCCG_B200_VEC");
+    mode = (e && std::atoi(e) == 2) ? 2 : 4;
+  }
+  return mode == 4 && aligned32(a) && aligned32(b) && aligned32(c);
+}
 
 // Whole-matrix SpMV (+ optional fused x.y) in one launch.
 static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool dot, const FinishParams &fp,
@@ -1285,7 +1295,10 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       if (k == 1) {
         HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
       } else if (defer_x) {
-        p_update_x_kernel<<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
+        if (use_vec4(m->r, m->p, rk[q].x))
+          p_update_x_kernel<4><<<stream_grid((m->n + 3) / 4), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
+        else
+          p_update_x_kernel<2><<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
         count_launch();
         HPCCG_LAUNCH_CHECK();
       } else {
@@ -1341,10 +1354,14 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       timers.tick(T_FUSED_UPD);
       for (int q = 0; q < L; ++q) {
         hpccg_dev_matrix *m = rk[q].m;
-        const int grid = stream_grid((m->n + 1) / 2);
-        if (defer_x)
-          update_r_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
-                                                         fp_for(FIN_RR, q, k, last, true));
+        const bool v4 = defer_x && use_vec4(m->Ap, m->r, m->r);
+        const int grid = stream_grid(v4 ? (m->n + 3) / 4 : (m->n + 1) / 2);
+        if (v4)
+          update_r_dot_kernel<4><<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
+                                                            fp_for(FIN_RR, q, k, last, true));
+        else if (defer_x)
+          update_r_dot_kernel<2><<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
+                                                            fp_for(FIN_RR, q, k, last, true));
         else
           update_xr_dot_kernel<<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->p, m->Ap, rk[q].x, m->r, m->partials, grid,
                                                           &m->state->counter, fp_for(FIN_RR, q, k, last, true));

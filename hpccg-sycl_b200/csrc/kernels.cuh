@@ -791,6 +791,26 @@ update_xr_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ 
 // SpMV updates r and reduces r.r (24 B/row), the p-update applies the previous iteration's x update and forms the new p
 // (40 B/row) -- 64 B/row instead of 48 + 24, every element still computed by the same two un-contracted operations.
 // The update of the last executed iteration is applied by x_fixup_kernel when the loop has ended.
+// 256-bit accesses (LDG.256 / STG.256, new with sm_100) for the two vector kernels of the loop: 4 doubles per thread and
+// stream, half the memory instructions of the 128-bit form.  Pointers must be 32-byte aligned (the launcher checks).
+struct double4v {
+  double a, b, c, d;
+};
+__device__ __forceinline__ double4v ld_stream_f64x4(const double *p) {
+  double4v v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double4v ld_f64x4(const double *p) {
+  double4v v;
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_f64x4(double *p, const double4v &v) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
+}
+
+template <int VEC>  // 2: 128-bit accesses, 4: 256-bit
 __global__ void __launch_bounds__(kThreads)
 update_r_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ Ap, double *__restrict__ r, double *partials,
                     int total_partials, unsigned *counter, FinishParams fp) {
@@ -798,51 +818,82 @@ update_r_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ A
   if (fp.check_active && fp.st->active == 0) return;
   const double nalpha = -(*alpha_dev);
   double acc = 0.0;
-  const int npair = n >> 1;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
-    const long long e = 2 * (long long)i;
-    const double2 av = ld_stream_f64x2(Ap + e);
-    double2 rv = *reinterpret_cast<const double2 *>(r + e);
-    rv.x = __dadd_rn(rv.x, __dmul_rn(nalpha, av.x));
-    rv.y = __dadd_rn(rv.y, __dmul_rn(nalpha, av.y));
-    *reinterpret_cast<double2 *>(r + e) = rv;
-    acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
-    acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
+  const int nvec = n / VEC;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nvec; i += gridDim.x * kThreads) {
+    const long long e = (long long)VEC * i;
+    if (VEC == 4) {
+      const double4v av = ld_stream_f64x4(Ap + e);
+      double4v rv = ld_f64x4(r + e);
+      rv.a = __dadd_rn(rv.a, __dmul_rn(nalpha, av.a));
+      rv.b = __dadd_rn(rv.b, __dmul_rn(nalpha, av.b));
+      rv.c = __dadd_rn(rv.c, __dmul_rn(nalpha, av.c));
+      rv.d = __dadd_rn(rv.d, __dmul_rn(nalpha, av.d));
+      st_f64x4(r + e, rv);
+      acc = __dadd_rn(acc, __dmul_rn(rv.a, rv.a));
+      acc = __dadd_rn(acc, __dmul_rn(rv.b, rv.b));
+      acc = __dadd_rn(acc, __dmul_rn(rv.c, rv.c));
+      acc = __dadd_rn(acc, __dmul_rn(rv.d, rv.d));
+    } else {
+      const double2 av = ld_stream_f64x2(Ap + e);
+      double2 rv = *reinterpret_cast<const double2 *>(r + e);
+      rv.x = __dadd_rn(rv.x, __dmul_rn(nalpha, av.x));
+      rv.y = __dadd_rn(rv.y, __dmul_rn(nalpha, av.y));
+      *reinterpret_cast<double2 *>(r + e) = rv;
+      acc = __dadd_rn(acc, __dmul_rn(rv.x, rv.x));
+      acc = __dadd_rn(acc, __dmul_rn(rv.y, rv.y));
+    }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int i = n - 1;
-    const double rn = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
-    r[i] = rn;
-    acc = __dadd_rn(acc, __dmul_rn(rn, rn));
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = nvec * VEC; i < n; ++i) {  // tail (n not a multiple of VEC)
+      const double rn = __dadd_rn(r[i], __dmul_rn(nalpha, Ap[i]));
+      r[i] = rn;
+      acc = __dadd_rn(acc, __dmul_rn(rn, rn));
+    }
   const double total = block_sum(acc, smem);
   publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
 }
 
 // x += alpha_{k-1} p_{k-1} (deferred HPCCG.cpp:383) ; p_k = r + beta p_{k-1} (HPCCG.cpp:369).  alpha, beta from the device state.
+template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 p_update_x_kernel(int n, const CgState *st, const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x) {
   if (st->active == 0) return;
   const double alpha = st->alpha, beta = st->beta;
-  const int npair = n >> 1;
-  for (int i = blockIdx.x * kThreads + threadIdx.x; i < npair; i += gridDim.x * kThreads) {
-    const long long e = 2 * (long long)i;
-    const double2 rv = ld_stream_f64x2(r + e);
-    double2 pv = *reinterpret_cast<const double2 *>(p + e);
-    double2 xv = *reinterpret_cast<const double2 *>(x + e);
-    xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
-    xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
-    pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
-    pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
-    *reinterpret_cast<double2 *>(x + e) = xv;
-    *reinterpret_cast<double2 *>(p + e) = pv;
+  const int nvec = n / VEC;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nvec; i += gridDim.x * kThreads) {
+    const long long e = (long long)VEC * i;
+    if (VEC == 4) {
+      const double4v rv = ld_stream_f64x4(r + e);
+      double4v pv = ld_f64x4(p + e);
+      double4v xv = ld_f64x4(x + e);
+      xv.a = __dadd_rn(xv.a, __dmul_rn(alpha, pv.a));
+      xv.b = __dadd_rn(xv.b, __dmul_rn(alpha, pv.b));
+      xv.c = __dadd_rn(xv.c, __dmul_rn(alpha, pv.c));
+      xv.d = __dadd_rn(xv.d, __dmul_rn(alpha, pv.d));
+      pv.a = __dadd_rn(rv.a, __dmul_rn(beta, pv.a));
+      pv.b = __dadd_rn(rv.b, __dmul_rn(beta, pv.b));
+      pv.c = __dadd_rn(rv.c, __dmul_rn(beta, pv.c));
+      pv.d = __dadd_rn(rv.d, __dmul_rn(beta, pv.d));
+      st_f64x4(x + e, xv);
+      st_f64x4(p + e, pv);
+    } else {
+      const double2 rv = ld_stream_f64x2(r + e);
+      double2 pv = *reinterpret_cast<const double2 *>(p + e);
+      double2 xv = *reinterpret_cast<const double2 *>(x + e);
+      xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+      xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+      pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
+      pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
+      *reinterpret_cast<double2 *>(x + e) = xv;
+      *reinterpret_cast<double2 *>(p + e) = pv;
+    }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const int i = n - 1;
-    const double po = p[i];
-    x[i] = __dadd_rn(x[i], __dmul_rn(alpha, po));
-    p[i] = __dadd_rn(r[i], __dmul_rn(beta, po));
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = nvec * VEC; i < n; ++i) {
+      const double po = p[i];
+      x[i] = __dadd_rn(x[i], __dmul_rn(alpha, po));
+      p[i] = __dadd_rn(r[i], __dmul_rn(beta, po));
+    }
 }
 
 // After the loop: the x update of the last executed iteration (niters >= 1), HPCCG.cpp:383.
