@@ -135,6 +135,29 @@ def test_short_iteration_counts(H, refwrap, cuda, max_iter):
     A.destroy()
 
 
+def test_solve_with_16_byte_aligned_vectors(H, refwrap, cuda):
+    """b and x that are 16- but not 32-byte aligned take the 128-bit form of the vector kernels; same history bar."""
+    torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(27, True)
+    A = H.generate_matrix(33, 17, 5)
+    m = A.device()
+    n = A.local_nrow
+    bb = torch.zeros(n + 6, dtype=torch.float64, device="cuda")
+    xx = torch.zeros(n + 6, dtype=torch.float64, device="cuda")
+    off = 2 if bb.data_ptr() % 32 == 0 else 4  # make the slices 16- but not 32-byte aligned
+    b, x = bb[off:off + n], xx[off:off + n]
+    assert b.data_ptr() % 32 == 16 and x.data_ptr() % 32 == 16
+    b.copy_(torch.from_numpy(A.b))
+    out = H.dev.cg_solve(m, b, x, 150, 0.0)
+    with refwrap.RefWorld(33, 17, 5, variant=ref_variant()) as R:
+        ref = R.solve(150)
+    check_history(out["hist"], ref["hist"], out["niters"], ref["niters"])
+    check_solution(x.cpu().numpy(), ref["x"][0])
+    assert xx[:off].abs().max().item() == 0.0 and xx[off + n:].abs().max().item() == 0.0  # nothing written outside x
+    A.destroy()
+
+
 def test_graph_replay_of_repeated_solves_is_bit_identical(H, refwrap, cuda):
     """HPCCG_SOLVE_GRAPH (what HPCCG() uses below 2^20 rows): the first solve with a key runs directly, the second is
     captured into a CUDA graph, later ones replay it.  Same kernels, same grids, same reduction trees -> same bits."""
