@@ -22,6 +22,7 @@
 #include "context.hpp"
 #include "device_matrix.hpp"
 #include "include/YAML_Doc.hpp"
+#include "include/dump_matlab_matrix.hpp"
 #include "include/hpccg_api.hpp"
 
 using namespace hpccg;
@@ -673,6 +674,20 @@ void free_vectors(double *x, double *b, double *xexact) {
   release_vector(x);
   release_vector(b);
   release_vector(xexact);
+}
+
+int dump_matlab_matrix(HPC_Sparse_Matrix *A, int rank) {
+  if (!A || !A->host_rows) return 1;
+  if (rank < 0 || rank > 3) return 0;  // the reference writes files for the first four ranks only
+  const std::string name = "mat" + std::to_string(rank) + ".dat";
+  FILE *f = std::fopen(name.c_str(), "w");
+  if (!f) return 1;
+  const long long first = (long long)A->local_nrow * rank;  // the reference's "chimney stack" row offset (:60)
+  for (int i = 0; i < A->local_nrow; ++i)
+    for (int j = 0; j < A->nnz_in_row[i]; ++j)
+      std::fprintf(f, " %lld %d %22.16e\n", first + i + 1, A->ptr_to_inds_in_row[i][j] + 1, A->ptr_to_vals_in_row[i][j]);
+  std::fclose(f);
+  return 0;
 }
 
 double mytimer(void) {

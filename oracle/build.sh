@@ -80,3 +80,17 @@ BASE="-O3 -DWALL -fPIC -w"
 build_variant serial "$BASE -DREF_VARIANT=0" "$COMMON_TUS" "$SED_NONE"
 build_variant omp "-O3 -funroll-all-loops -malign-double -fopenmp -DUSING_OMP -DWALL -fPIC -w -DREF_VARIANT=1" "$COMMON_TUS" "$SED_NONE"
 build_variant mpi "$BASE -DUSING_MPI -Impi_shim -DREF_VARIANT=2" "$COMMON_TUS $MPI_TUS" "$SED_MAXEXT"
+
+# ---- (3) the reference's OWN main.cpp on the B200 library (drop-in proof, tests/test_gpu_cli.py) ----------------
+# /root/reference/main.cpp, unmodified, compiled against hpccg-sycl_b200/csrc/include (the reference's header names) and
+# linked with libhpccg_b200.so instead of the reference's kernels.  Nothing of the reference but main() is in this binary.
+B200_LIB=../hpccg-sycl_b200/lib
+if [ -f "$B200_LIB/libhpccg_b200.so" ]; then
+  if [ ! -f "$OUT/test_HPCCG_refmain" ] || [ "$B200_LIB/libhpccg_b200.so" -nt "$OUT/test_HPCCG_refmain" ]; then
+    # read from stdin: a quoted #include then looks in the -I directories (this repo's headers under the reference's
+    # names), not next to main.cpp where the reference's own headers lie
+    "$CXX" -O2 -DWALL -w -I../hpccg-sycl_b200/csrc/include -I../include -x c++ - -o "$OUT/test_HPCCG_refmain" \
+      -L"$B200_LIB" -lhpccg_b200 -Wl,-rpath,'$ORIGIN/../../hpccg-sycl_b200/lib' < "$REF/main.cpp"
+    echo "built $OUT/test_HPCCG_refmain (reference main.cpp + libhpccg_b200.so)"
+  fi
+fi

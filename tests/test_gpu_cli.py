@@ -72,3 +72,25 @@ def test_cli_mode2_matrix_file(H, refwrap, cuda, tmp_path):
     assert "Initial Residual = 258.24\n" in res.stdout and "Iteration = 15   Residual = 2.15402e-06\n" in res.stdout
     assert "Number of iterations: 149\n" in res.stdout
     assert run([str(tmp_path / "nope.dat")], tmp_path).returncode == 1
+
+
+def test_reference_main_cpp_runs_on_the_b200_library(H, refwrap, cuda, tmp_path):
+    """Drop-in proof: oracle/_ref/test_HPCCG_refmain is the reference's OWN, unmodified main.cpp (read where it lies under
+    /root/reference by oracle/build.sh) compiled against this repo's headers (the reference's header names) and linked with
+    libhpccg_b200.so instead of the reference's kernels.  main.cpp hard-codes max_iter = 500 (main.cpp:187)."""
+    exe = ROOT / "oracle" / "_ref" / "test_HPCCG_refmain"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/test_HPCCG_refmain not built (needs /root/reference at build time)")
+    res = subprocess.run([str(exe), "64", "64", "64"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    out = res.stdout
+    with refwrap.RefWorld(64, 64, 64, variant="serial" if refwrap.available("serial") else "oracle") as R:
+        ref = R.solve(500, hist=False)
+        href = R.solve(500, hist=True)["hist"]
+    assert "Error in call to CG" not in res.stderr
+    assert "Initial Residual = 1654.81\n" in out                       # SURVEY.md 4.1: 1654.8087502790163
+    m = re.search(r"Iteration = 50   Residual = (\S+)", out)            # print_freq = 50 at max_iter = 500 (HPCCG.cpp:342-343)
+    assert m and abs(float(m.group(1)) - href[50]) <= 1e-5 * href[50]  # 6 printed digits
+    m = re.search(r"Number of iterations: (\d+)", out)
+    assert m and int(m.group(1)) == ref["niters"] == 499
+    assert "  nx: 64\n" in out and "MFLOPS Summary: \n" in out and "  SPARSEMV: " in out
