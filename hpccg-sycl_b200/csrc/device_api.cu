@@ -1153,7 +1153,17 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   timers.reset();
   timers.on = (flags & HPCCG_SOLVE_TIMERS) != 0 && times != nullptr;
   timers.s = s;
-  cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
+  // released on every return path
+  struct LoopResources {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int *h_active = nullptr;
+    ~LoopResources() {
+      if (ev0) cudaEventDestroy(ev0);
+      if (ev1) cudaEventDestroy(ev1);
+      if (h_active) cudaFreeHost(h_active);
+    }
+  } res;
+  cudaEvent_t &ev_loop0 = res.ev0, &ev_loop1 = res.ev1;
   if (!capture_only) {
     HPCCG_CUDA(cudaEventCreate(&ev_loop0));
     HPCCG_CUDA(cudaEventCreate(&ev_loop1));
@@ -1269,7 +1279,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 
   // ---- iterations (HPCCG.cpp:358-386) ----
   if (!capture_only) HPCCG_CUDA(cudaEventRecord(ev_loop0, s));
-  int *h_active = nullptr;
+  int *&h_active = res.h_active;
   if (tol > 0.0 && !capture_only) HPCCG_CUDA(cudaMallocHost(&h_active, sizeof(int)));
   for (int k = 1; k < max_iter; ++k) {
     const int last = (k + 1 == max_iter) ? 1 : 0;
@@ -1396,7 +1406,6 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   }
   if (capture_only) return 0;
   HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
-  if (h_active) cudaFreeHost(h_active);
 
   // ---- results ----
   CgState hs;
@@ -1410,8 +1419,6 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   float ms = 0.f;
   HPCCG_CUDA(cudaEventElapsedTime(&ms, ev_loop0, ev_loop1));
   if (loop_ms) *loop_ms = ms;
-  cudaEventDestroy(ev_loop0);
-  cudaEventDestroy(ev_loop1);
   if (times) {
     double acc[16] = {0};
     timers.collect(acc, 16);
