@@ -1494,23 +1494,27 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
     }
   }
   // order the replay after whatever the caller enqueued on its stream (b, x uploads), and time it as a whole
-  cudaEvent_t ev_in = nullptr, ev0 = nullptr, ev1 = nullptr;
-  HPCCG_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-  HPCCG_CUDA(cudaEventCreate(&ev0));
-  HPCCG_CUDA(cudaEventCreate(&ev1));
-  HPCCG_CUDA(cudaEventRecord(ev_in, (cudaStream_t)stream));
-  HPCCG_CUDA(cudaStreamWaitEvent(gs, ev_in, 0));
-  HPCCG_CUDA(cudaEventRecord(ev0, gs));
+  struct ReplayEvents {
+    cudaEvent_t in = nullptr, t0 = nullptr, t1 = nullptr;
+    ~ReplayEvents() {
+      if (in) cudaEventDestroy(in);
+      if (t0) cudaEventDestroy(t0);
+      if (t1) cudaEventDestroy(t1);
+    }
+  } ev;
+  HPCCG_CUDA(cudaEventCreateWithFlags(&ev.in, cudaEventDisableTiming));
+  HPCCG_CUDA(cudaEventCreate(&ev.t0));
+  HPCCG_CUDA(cudaEventCreate(&ev.t1));
+  HPCCG_CUDA(cudaEventRecord(ev.in, (cudaStream_t)stream));
+  HPCCG_CUDA(cudaStreamWaitEvent(gs, ev.in, 0));
+  HPCCG_CUDA(cudaEventRecord(ev.t0, gs));
   HPCCG_CUDA(cudaGraphLaunch(m->graph_exec, gs));
-  count_launch(3 * (max_iter - 1) + 4);
-  HPCCG_CUDA(cudaEventRecord(ev1, gs));
+  count_launch(3 * (max_iter - 1) + 5);
+  HPCCG_CUDA(cudaEventRecord(ev.t1, gs));
   HPCCG_TRY(solve_readback(m, max_iter, niters, normr, hist_host, nullptr, gs));
   float ms = 0.f;
-  HPCCG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  HPCCG_CUDA(cudaEventElapsedTime(&ms, ev.t0, ev.t1));
   if (loop_ms) *loop_ms = ms;
-  cudaEventDestroy(ev_in);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   return 0;
 }
 
