@@ -229,6 +229,10 @@ def run_cpu_reference(w: dict, iters: int, steps: int, warmup: int):
 def reference_arm(args, w: dict, config: dict, rank: int, size: int):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers unless the user set it; the reference arm is meant to use all
+    # the host threads it can (libgomp reads the variable when the reference library is loaded, i.e. later)
+    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     # a bounded sample: the driver passes the GPU arm's --steps/--warmup; keep the run within a few minutes
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     rates, info = run_cpu_reference(w, args.cpu_iters, steps, warmup)

@@ -46,7 +46,11 @@ def test_reference_arm_under_torchrun(H):
            "--ny", "32", "--nz", "16", "--steps", "1", "--warmup", "1", "--cpu-iters", "5"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
-    check_line(res.stdout, 2)
+    d = check_line(res.stdout, 2)
+    import os
+    # torchrun's OMP_NUM_THREADS=1 default must not throttle the reference: all host threads, as at N = 1
+    if d["cpu_baseline"]["variant"] == "omp":
+        assert d["cpu_baseline"]["cores"] == os.cpu_count()
 
 
 def test_gpu_arm_refuses_without_gpu(H):
