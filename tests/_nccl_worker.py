@@ -59,6 +59,13 @@ def main():
             worst = check_history(hist, ref["hist"], niters, ref["niters"])
             check_solution(x, ref["x"][rank])
         os.environ["HPCCG_B200_UNFUSED"] = "0"
+        # `normr > tolerance` ends the loop at the same iteration on every rank (HPCCG.cpp:358); the kernels enqueued after
+        # that return at once on all ranks alike, so nobody is left waiting for a peer
+        with refwrap.RefWorld(*dims, size=size, stencil=stencil, variant=variant) as R:
+            rt = R.solve(150, 1e-3)
+        x = A.x.copy()
+        nit, nr, _, _ = H.HPCCG(A, A.b, x, 150, 1e-3)
+        assert nit == rt["niters"] and abs(nr - rt["normr"]) <= 1e-8 * rt["normr"], (nit, rt["niters"], nr, rt["normr"])
         mine = xs[rank].copy()
         H.exchange_externals(A, mine)
         y = np.empty(n)
