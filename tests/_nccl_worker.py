@@ -63,8 +63,8 @@ def main():
         # that return at once on all ranks alike, so nobody is left waiting for a peer
         with refwrap.RefWorld(*dims, size=size, stencil=stencil, variant=variant) as R:
             rt = R.solve(150, 1e-3)
-        x = A.x.copy()
-        nit, nr, _, _ = H.HPCCG(A, A.b, x, 150, 1e-3)
+        xt = A.x.copy()
+        nit, nr, _, _ = H.HPCCG(A, A.b, xt, 150, 1e-3)
         assert nit == rt["niters"] and abs(nr - rt["normr"]) <= 1e-8 * rt["normr"], (nit, rt["niters"], nr, rt["normr"])
         mine = xs[rank].copy()
         H.exchange_externals(A, mine)
