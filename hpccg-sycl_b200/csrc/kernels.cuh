@@ -151,7 +151,8 @@ __device__ __forceinline__ double peer_allreduce(PeerLink *pl, double local, dou
     st_release_sys(&dst->seq[slot][pl->rank], seq);
     Mailbox *own = pl->box[pl->rank];
     double v;
-    if (peer_wait_ge(&own->seq[slot][t], seq)) {
+    // once a wait has timed out the job is lost: later waits give up at once, so a dead peer costs one time-out, not one per kernel
+    if (*reinterpret_cast<volatile int *>(&pl->error) == 0 && peer_wait_ge(&own->seq[slot][t], seq)) {
       v = *reinterpret_cast<volatile double *>(&own->value[slot][t]);
     } else {
       pl->error = 1;
@@ -420,7 +421,8 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
       // the neighbours' planes for THIS exchange (stamp = the number the local halo_put_kernel just took) must have landed
       if (tid < halo.link->nnb) {
         const Mailbox *own = halo.link->box[halo.link->rank];
-        if (!peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq)) halo.link->error = 2;
+        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq))
+          halo.link->error = 2;
       }
       __syncthreads();
       halo_ready = true;
@@ -515,7 +517,8 @@ spmv_pattern_kernel(const unsigned short *__restrict__ pat_id, const double *__r
     if (touches_halo && !halo_ready) {
       if (tid < halo.link->nnb) {
         const Mailbox *own = halo.link->box[halo.link->rank];
-        if (!peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq)) halo.link->error = 2;
+        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq))
+          halo.link->error = 2;
       }
       __syncthreads();
       halo_ready = true;
