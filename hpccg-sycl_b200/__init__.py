@@ -129,6 +129,12 @@ class DeviceMatrix:
         check(lib.hpccg_dev_matrix_format(self.handle, C.byref(f), C.byref(p)))
         return {"format": f.value, "patterns": p.value}
 
+    def comm(self) -> dict:
+        """Data plane of the multi-rank solves on this mirror: peer memory inside the kernels or NCCL between them."""
+        p, f = C.c_int(), C.c_int()
+        check(lib.hpccg_dev_matrix_comm(self.handle, C.byref(p), C.byref(f)))
+        return {"peer": bool(p.value), "fused_put": bool(f.value)}
+
     def bytes(self) -> int:
         b = C.c_longlong()
         check(lib.hpccg_dev_matrix_bytes(self.handle, C.byref(b)))

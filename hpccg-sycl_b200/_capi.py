@@ -53,6 +53,7 @@ SIGNATURES = {
     "hpccg_dev_matrix_bytes": (C.c_int, [VP, PLL]),
     "hpccg_dev_matrix_compress": (C.c_int, [VP]),
     "hpccg_dev_matrix_format": (C.c_int, [VP, PI, PI]),
+    "hpccg_dev_matrix_comm": (C.c_int, [VP, PI, PI]),
     "hpccg_dev_spmv": (C.c_int, [VP, VP, VP, VP]),
     "hpccg_dev_dot": (C.c_int, [C.c_int, VP, VP, VP, VP]),
     "hpccg_dev_waxpby": (C.c_int, [C.c_int, C.c_double, VP, C.c_double, VP, VP, VP]),

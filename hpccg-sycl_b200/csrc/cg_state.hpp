@@ -71,10 +71,32 @@ struct PeerLink {
   double *nb_dst[kMaxPeerNb];               // where my send segment i lands inside neighbour i's p vector
   unsigned long long *nb_flag[kMaxPeerNb];  // neighbour i's halo_seq entry for me
   int seg_start[kMaxPeerNb + 1];            // segment boundaries of elements_to_send
-  unsigned long long reduce_seq;            // device-local counters; identical on every rank by construction
-  unsigned long long halo_seq;
-  unsigned int ticket;
+  unsigned long long reduce_seq;            // device-local counter; identical on every rank by construction
+  unsigned long long epoch;                 // solves started on this matrix (cg_state_init_kernel); same on every rank
+  unsigned int ticket;                      // stand-alone halo_put_kernel: last-block ticket
+  unsigned int put_ticket[kMaxPeerNb];      // fused put (p_update_x_kernel): per-segment ticket of the contributing CTAs
   unsigned int pad;
+};
+
+// Stamp of exchange number `idx` (1 = the set-up exchange, k + 1 = iteration k) of the current solve.  It is a function of
+// device state (epoch) and of a launch-position constant (idx), so a captured CUDA graph replays with fresh stamps.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline unsigned long long exchange_stamp(unsigned long long epoch, int idx) {
+  return (epoch << 32) | (unsigned long long)(unsigned int)idx;
+}
+
+// exchange_externals.cpp:103-112 folded into the kernel that PRODUCES p: per send segment (= neighbour) an inverse map
+// row -> position in the neighbour's halo tail over the row range [lo, hi) the segment draws from, so the thread that
+// writes p[row] also stores it across NVLink.  nseg == 0: no put.
+struct HaloPut {
+  PeerLink *link;
+  const int *inv;                 // concatenated inverse maps, -1 = row not sent to this neighbour
+  int nseg;
+  int exch_idx;
+  int lo[kMaxPeerNb], hi[kMaxPeerNb], inv_off[kMaxPeerNb];
+  double *dst[kMaxPeerNb];        // neighbour's p + its halo offset for my segment (IPC-mapped)
 };
 
 }  // namespace hpccg

@@ -189,13 +189,13 @@ void peer_link_destroy(hpccg_dev_matrix *m) {
   m->mailbox = nullptr;
 }
 
-int peer_link_create(hpccg_dev_matrix *m) {
+int peer_link_create(hpccg_dev_matrix *m, bool eligible) {
   if (m->peer_tried) return 0;
   m->peer_tried = 1;
   const int R = g_comm_size, me = g_comm_rank;
   PeerCard mine;
   std::memset(&mine, 0, sizeof mine);
-  mine.ok = (R <= kMaxRanks && m->num_neighbors <= kMaxPeerNb && m->p != nullptr) ? 1 : 0;
+  mine.ok = (eligible && R <= kMaxRanks && m->num_neighbors <= kMaxPeerNb && m->p != nullptr) ? 1 : 0;
   if (const char *e = std::getenv("HPCCG_B200_COMM"))
     if (std::string(e) == "nccl") mine.ok = 0;  // A/B switch: NCCL send/recv + gathers
   if (mine.ok) {
@@ -297,6 +297,9 @@ int peer_link_create(hpccg_dev_matrix *m) {
   }
   HPCCG_CUDA(cudaMalloc(&m->peer_link, sizeof(PeerLink)));
   HPCCG_CUDA(cudaMemcpy(m->peer_link, &h, sizeof h, cudaMemcpyHostToDevice));
+  // the put folded into the p-producing kernel receives the link and the remote destinations as kernel parameters
+  m->put_plan.link = m->peer_link;
+  for (int i = 0; i < kMaxPeerNb; ++i) m->put_plan.dst[i] = h.nb_dst[i];
   return 0;
 }
 

@@ -44,7 +44,9 @@ struct hpccg_dev_matrix;
 namespace hpccg {
 // Builds m->peer_link for the calling rank (collective over the NCCL communicator): exchanges IPC handles of every
 // rank's mailbox and p vector, maps the peers' memory and resolves where each send segment lands in its neighbour's p.
+// `eligible`: this rank's matrix can be served by the kernels that wait on peer memory; the link exists only when EVERY
+// rank is eligible.  Must be called by all ranks of the communicator or by none (it contains collectives).
 // Leaves m->peer_link == nullptr (NCCL path) when peer memory cannot be used; returns non-zero only on hard errors.
-int peer_link_create(hpccg_dev_matrix *m);
+int peer_link_create(hpccg_dev_matrix *m, bool eligible);
 void peer_link_destroy(hpccg_dev_matrix *m);
 }  // namespace hpccg

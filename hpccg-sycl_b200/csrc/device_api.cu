@@ -45,22 +45,41 @@ int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 // ---- device info ---------------------------------------------------------------------------------------
-static Device g_dev;
-static std::once_flag g_dev_once;
+// Everything cached here is PER DEVICE (a process may drive several GPUs through hpccg_set_device): the SM count, and
+// below the occupancy results and the MaxDynamicSharedMemorySize opt-in, which CUDA keeps per device as well.
+constexpr int kMaxDevices = 16;
+static Device g_dev[kMaxDevices];
+static std::atomic<int> g_dev_known[kMaxDevices];
+
+static int current_device_slot() {
+  int id = 0;
+  if (cudaGetDevice(&id) != cudaSuccess) {
+    cudaGetLastError();
+    id = 0;
+  }
+  return (id >= 0 && id < kMaxDevices) ? id : 0;
+}
 
 const Device &device_info() {
-  std::call_once(g_dev_once, [] {
-    int id = 0;
-    if (cudaGetDevice(&id) == cudaSuccess) {
-      cudaDeviceProp prop;
-      if (cudaGetDeviceProperties(&prop, id) == cudaSuccess) {
-        g_dev.sm_count = prop.multiProcessorCount;
-        g_dev.id = id;
-      }
-    }
-  });
-  return g_dev;
+  const int id = current_device_slot();
+  if (!g_dev_known[id].load(std::memory_order_acquire)) {
+    Device d;
+    d.id = id;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, id) == cudaSuccess && sms > 0) d.sm_count = sms;
+    else cudaGetLastError();
+    g_dev[id] = d;
+    g_dev_known[id].store(1, std::memory_order_release);
+  }
+  return g_dev[id];
 }
+
+// one int per device, 0 = not computed yet
+struct PerDeviceInt {
+  std::atomic<int> v[kMaxDevices];
+  int get() { return v[current_device_slot()].load(std::memory_order_relaxed); }
+  void set(int x) { v[current_device_slot()].store(x, std::memory_order_relaxed); }
+};
 
 int stream_grid(long long work_items, int blocks_per_sm) {
   long long blocks = (work_items + kThreads - 1) / kThreads;
@@ -120,6 +139,7 @@ int ensure_solver_workspace(hpccg_dev_matrix *m, int max_iter, int nranks) {
     HPCCG_CUDA(cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
     HPCCG_CUDA(cudaEventCreateWithFlags(&m->ev_p_ready, cudaEventDisableTiming));
     HPCCG_CUDA(cudaEventCreateWithFlags(&m->ev_halo_done, cudaEventDisableTiming));
+    for (cudaEvent_t &e : m->ev_io) HPCCG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -142,16 +162,27 @@ static int alloc_common(hpccg_dev_matrix *m) {
   HPCCG_CUDA(cudaMalloc(&m->cols, sizeof(int) * (size_t)m->slots * m->npad));
   HPCCG_CUDA(cudaMalloc(&m->partials, sizeof(double) * kMaxPartials));
   HPCCG_CUDA(cudaMalloc(&m->state, sizeof(CgState)));
-  cg_state_init_kernel<<<1, 32>>>(m->state);
+  cg_state_init_kernel<<<1, 32>>>(m->state, nullptr);
   count_launch();
   HPCCG_LAUNCH_CHECK();
   return 0;
 }
 
+// Buffers a captured solve graph points at are about to change (format switch, new halo plan): drop the graph.
+static void invalidate_graph(hpccg_dev_matrix *m) {
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  m->graph_exec = nullptr;
+  m->graph_b = nullptr;
+  m->graph_x = nullptr;
+  m->graph_max_iter = 0;
+  ++m->generation;
+}
+
 // ---- SpMV launch ----------------------------------------------------------------------------------------
 template <int SLOTS, int RPT, bool DOT>
 static int spmv_occupancy_grid() {
-  static int cached = 0;
+  static PerDeviceInt cache;
+  int cached = cache.get();
   if (cached) return cached;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_ell_kernel<SLOTS, RPT, DOT>, kThreads, 0) != cudaSuccess ||
@@ -159,6 +190,7 @@ static int spmv_occupancy_grid() {
     per_sm = 2;
   cached = per_sm * device_info().sm_count;
   if (cached > kMaxPartials / 4) cached = kMaxPartials / 4;  // room for interior + two boundary launches
+  cache.set(cached);
   return cached;
 }
 
@@ -228,7 +260,8 @@ static int tma_l2_ahead() {
 
 template <int SLOTS, int SPS, int NSTAGES, bool DOT>
 static int tma_ctas_per_sm() {
-  static int cached = 0;
+  static PerDeviceInt cache;
+  int cached = cache.get();
   if (cached) return cached;
   using Cfg = SpmvTmaCfg<SLOTS, SPS, NSTAGES>;
   auto kern = spmv_sell_tma_kernel<SLOTS, SPS, NSTAGES, DOT>;
@@ -237,6 +270,7 @@ static int tma_ctas_per_sm() {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::kRows, Cfg::kSmemBytes) != cudaSuccess || per_sm < 1)
     return -1;
   cached = per_sm;
+  cache.set(cached);
   return cached;
 }
 
@@ -301,12 +335,14 @@ static int tma_variant() {
 // ---- pattern-coded format: tiles of kThreads rows, persistent CTAs ------------------------------------------------
 template <int SLOTS, bool DOT>
 static int pattern_ctas_per_sm() {
-  static int cached = 0;
+  static PerDeviceInt cache;
+  int cached = cache.get();
   if (cached) return cached;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_kernel<SLOTS, DOT>, kThreads, 0) != cudaSuccess || per_sm < 1)
     per_sm = 2;
   cached = per_sm;
+  cache.set(cached);
   return cached;
 }
 
@@ -682,10 +718,59 @@ int hpccg_dev_matrix_set_halo(hpccg_dev_matrix *m, int num_neighbors, const int 
   m->recv_length.assign(recv_length, recv_length + num_neighbors);
   m->send_length.assign(send_length, send_length + num_neighbors);
   m->total_to_be_sent = total_to_be_sent;
+  invalidate_graph(m);
   if (m->d_elements_to_send) HPCCG_CUDA(cudaFree(m->d_elements_to_send));
   if (m->d_send_buffer) HPCCG_CUDA(cudaFree(m->d_send_buffer));
+  if (m->d_put_inv) HPCCG_CUDA(cudaFree(m->d_put_inv));
   m->d_elements_to_send = nullptr;
   m->d_send_buffer = nullptr;
+  m->d_put_inv = nullptr;
+  m->put_fusable = 0;
+  m->put_plan = HaloPut{};
+  // Inverse send maps (row -> position in the neighbour's halo tail), one per neighbour, over the row range the segment
+  // draws from: what lets the p-producing kernel do the put itself.  z-slabs send one boundary plane per neighbour (a
+  // permutation of a contiguous row range in the 27-pt case, make_local_matrix.cpp:218-230), so the maps are exactly
+  // plane-sized; a scattered or repeating send list keeps the stand-alone put kernel.
+  if (num_neighbors > 0 && num_neighbors <= kMaxPeerNb) {
+    std::vector<int> inv;
+    bool ok = true;
+    int seg = 0;
+    for (int i = 0; i < num_neighbors && ok; ++i) {
+      const int len = send_length[i];
+      int lo = 0, hi = 0;
+      if (len > 0) {
+        lo = elements_to_send[seg];
+        hi = lo + 1;
+        for (int k = 0; k < len; ++k) {
+          const int e = elements_to_send[seg + k];
+          if (e < 0 || e >= m->n) return fail(HPCCG_ERR_ARG, "elements_to_send[%d] = %d outside local rows", seg + k, e);
+          lo = std::min(lo, e);
+          hi = std::max(hi, e + 1);
+        }
+        if ((long long)(hi - lo) > 4LL * len + 4096) ok = false;
+      }
+      m->put_plan.lo[i] = lo;
+      m->put_plan.hi[i] = hi;
+      m->put_plan.inv_off[i] = (int)inv.size();
+      if (ok && len > 0) {
+        const size_t base = inv.size();
+        inv.resize(base + (size_t)(hi - lo), -1);
+        for (int k = 0; k < len && ok; ++k) {
+          int &slot = inv[base + (size_t)(elements_to_send[seg + k] - lo)];
+          if (slot >= 0) ok = false;  // the same row twice for one neighbour: not a function
+          slot = k;
+        }
+      }
+      seg += len;
+    }
+    if (ok) {
+      HPCCG_CUDA(cudaMalloc(&m->d_put_inv, sizeof(int) * std::max<size_t>(inv.size(), 1)));
+      if (!inv.empty()) HPCCG_CUDA(cudaMemcpy(m->d_put_inv, inv.data(), sizeof(int) * inv.size(), cudaMemcpyHostToDevice));
+      m->put_plan.inv = m->d_put_inv;
+      m->put_plan.nseg = num_neighbors;
+      m->put_fusable = 1;
+    }
+  }
   if (total_to_be_sent > 0) {
     for (int i = 0; i < total_to_be_sent; ++i)
       if (elements_to_send[i] < 0 || elements_to_send[i] >= m->n)
@@ -707,6 +792,7 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->pat_len);
   cudaFree(m->d_elements_to_send);
   cudaFree(m->d_send_buffer);
+  cudaFree(m->d_put_inv);
   cudaFree(m->partials);
   cudaFree(m->state);
   cudaFree(m->gathered);
@@ -722,6 +808,8 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
   if (m->ev_p_ready) cudaEventDestroy(m->ev_p_ready);
   if (m->ev_halo_done) cudaEventDestroy(m->ev_halo_done);
+  for (cudaEvent_t e : m->ev_io)
+    if (e) cudaEventDestroy(e);
   delete m;
   return 0;
 }
@@ -781,6 +869,13 @@ int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *pattern
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
   if (format) *format = m->format;
   if (patterns) *patterns = m->npat;
+  return 0;
+}
+
+int hpccg_dev_matrix_comm(const hpccg_dev_matrix *m, int *peer, int *fused_put) {
+  if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
+  if (peer) *peer = m->peer_link ? 1 : 0;
+  if (fused_put) *fused_put = (m->peer_link && m->put_fusable && !std::getenv("HPCCG_B200_SEPARATE_PUT")) ? 1 : 0;
   return 0;
 }
 
@@ -882,6 +977,7 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
   cudaFree(ids);
   cudaFree(scal);
   cudaFree(rep);
+  invalidate_graph(m);  // a captured solve replays the SELL kernels on the arrays released here
   cudaFree(m->vals);
   cudaFree(m->cols);
   m->vals = nullptr;
@@ -1061,6 +1157,27 @@ static FinishParams make_fp(int mode, hpccg_dev_matrix *m, int k, int last, doub
   return fp;
 }
 
+// The kernel that produces p (kernels.cuh): mode 0 = waxpby copy p = src (HPCCG.cpp:347,362), mode 1 = deferred x update +
+// p = r + beta p (:383,:369); put != nullptr folds the peer-memory halo put of exchange `put->exch_idx` into it.
+template <int VEC, int MODE>
+static int launch_p_update_t(int n, const CgState *st, bool check, const double *src_r, double *p, double *x, const HaloPut *put,
+                             cudaStream_t s) {
+  const int grid = stream_grid((n + VEC - 1) / VEC);
+  if (put) p_update_x_kernel<VEC, MODE, true><<<grid, kThreads, 0, s>>>(n, st, check ? 1 : 0, src_r, p, x, *put);
+  else p_update_x_kernel<VEC, MODE, false><<<grid, kThreads, 0, s>>>(n, st, check ? 1 : 0, src_r, p, x, HaloPut{});
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_p_update(int mode, int n, const CgState *st, bool check, const double *src_r, double *p, double *x,
+                           const HaloPut *put, cudaStream_t s) {
+  if (n == 0) return 0;
+  const bool v4 = use_vec4(src_r, p, mode == 1 ? (const void *)x : (const void *)p);
+  if (mode == 1) return v4 ? launch_p_update_t<4, 1>(n, st, check, src_r, p, x, put, s) : launch_p_update_t<2, 1>(n, st, check, src_r, p, x, put, s);
+  return v4 ? launch_p_update_t<4, 0>(n, st, check, src_r, p, x, put, s) : launch_p_update_t<2, 0>(n, st, check, src_r, p, x, put, s);
+}
+
 // Halo exchange of vector v (ncol doubles) for all local ranks.  nccl: one local rank, transfers on the
 // matrix's comm stream (caller fences with events); otherwise every rank of the world is local and the
 // transfers are device copies on `s`.
@@ -1124,7 +1241,7 @@ static int solve_readback(hpccg_dev_matrix *m, int max_iter, int *niters_out, do
 
 static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_iter, double tol, int *niters_out,
                          double *normr_out, double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t s,
-                         bool capture_only = false) {
+                         bool capture_only = false, const SolveIO *io = nullptr) {
   const int L = (int)rk.size();
   const bool multi = R > 1;
   const bool unfused = (flags & HPCCG_SOLVE_UNFUSED) != 0;
@@ -1136,15 +1253,23 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     if (!aligned16(q.b) || !aligned16(q.x)) return fail(HPCCG_ERR_ARG, "cg_solve: b and x must be 16-byte aligned");
     if (multi && q.m->ncol > q.m->n && q.m->num_neighbors == 0)
       return fail(HPCCG_ERR_STATE, "cg_solve: matrix has halo columns but no halo plan (call make_local_matrix)");
+    // a localised matrix solved as a single rank would read a halo nobody fills (e.g. the rank context of another thread)
+    if (!multi && q.m->ncol > q.m->n)
+      return fail(HPCCG_ERR_STATE, "cg_solve: matrix has %d halo columns but this thread's rank context is 1 rank "
+                  "(hpccg_ctx_set / hpccg_nccl_init on this thread)", q.m->ncol - q.m->n);
     HPCCG_TRY(ensure_solver_workspace(q.m, max_iter, R));
   }
   // all local ranks share rank 0's gather array in the in-process world
   double *gathered = rk[0].m->gathered;
   // Multi-process runs: halos and scalar sums go through peer memory inside the kernels (PeerLink) when every rank
   // could map its peers and the matrix is served by the TMA SpMV; otherwise NCCL send/recv + gathers between kernels.
+  // peer_link_create is a COLLECTIVE (it allgathers over the NCCL communicator), so whether it is entered may depend only
+  // on things that are equal on every rank (the flags); whether THIS rank can serve the peer path -- its slot count has a
+  // TMA kernel, or it is pattern-coded -- travels inside the exchange as an eligibility bit and all ranks take one decision.
   PeerLink *link = nullptr;
-  if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY) && (use_tma_path(rk[0].m->slots) || rk[0].m->format == 1)) {
-    HPCCG_TRY(peer_link_create(rk[0].m));
+  if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY)) {
+    const bool eligible = use_tma_path(rk[0].m->slots) || rk[0].m->format == 1;
+    HPCCG_TRY(peer_link_create(rk[0].m, eligible));
     link = rk[0].m->peer_link;
   }
   const bool p2p = link != nullptr;
@@ -1201,16 +1326,24 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     fp.out = gathered + rk[q].grank;
     return fp;
   };
-  auto do_exchange = [&](bool check) -> int {
-    if (!multi) return 0;
+  // p2p with compact inverse send maps: the put rides in the kernel that produces p (no exchange launch at all)
+  // (the literal / eager-x sequences, kept for validation and A/B, use the stand-alone put kernel)
+  const bool fused_put = p2p && defer_x && rk[0].m->put_fusable && !std::getenv("HPCCG_B200_SEPARATE_PUT");
+  auto put_for = [&](int exch_idx) {
+    HaloPut hp = rk[0].m->put_plan;
+    hp.exch_idx = exch_idx;
+    return hp;
+  };
+  auto do_exchange = [&](bool check, int exch_idx) -> int {
+    if (!multi || fused_put) return 0;
     timers.tick(T_EXCH);
     if (p2p) {
       hpccg_dev_matrix *m = rk[0].m;
-      if (m->total_to_be_sent > 0) {
+      if (m->num_neighbors > 0) {
         // one element per thread: the remote stores are posted writes, so the kernel's length is one gather + one
         // NVLink round trip for the system-scope fence, not a per-thread chain of dependent iterations
         const int grid = std::max(1, std::min(2048, (m->total_to_be_sent + kThreads - 1) / kThreads));
-        halo_put_kernel<<<grid, kThreads, 0, s>>>(m->total_to_be_sent, m->d_elements_to_send, m->p, link, check ? m->state : nullptr);
+        halo_put_kernel<<<grid, kThreads, 0, s>>>(m->total_to_be_sent, m->d_elements_to_send, m->p, link, check ? m->state : nullptr, exch_idx);
         count_launch();
         HPCCG_LAUNCH_CHECK();
       }
@@ -1221,8 +1354,9 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     return 0;
   };
   SpmvHalo halo{};
-  if (p2p) halo = SpmvHalo{link, rk[0].m->n, rk[0].m->interior_begin, rk[0].m->interior_end};
+  if (p2p) halo = SpmvHalo{link, rk[0].m->n, rk[0].m->interior_begin, rk[0].m->interior_end, 0};
   auto spmv_dot_all = [&](int mode, int k, bool check, bool dot) -> int {
+    halo.exch_idx = k + 1;  // the exchange that precedes this SpMV (1 = set-up)
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
       FinishParams fp = dot ? fp_for(mode, q, k, 0, check) : make_fp(FIN_STORE, m, k, 0, tol, check);
@@ -1233,7 +1367,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 
   for (int q = 0; q < L; ++q) {
     hpccg_dev_matrix *m = rk[q].m;
-    cg_state_init_kernel<<<1, 32, 0, s>>>(m->state);
+    cg_state_init_kernel<<<1, 32, 0, s>>>(m->state, p2p ? link : nullptr);
     count_launch();
     HPCCG_CUDA(cudaMemsetAsync(m->hist, 0xFF, sizeof(double) * (max_iter + 1), s));  // NaN = "no iteration ran"
   }
@@ -1243,12 +1377,19 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 
   // ---- set-up: p = x ; Ap = A p ; r = b - Ap ; rtrans = r.r (HPCCG.cpp:347-354) ----
   timers.tick(T_WAXPBY);
-  for (int q = 0; q < L; ++q) HPCCG_TRY(launch_waxpby(rk[q].m->n, 1.0, rk[q].x, 0.0, nullptr, rk[q].x, rk[q].m->p, nullptr, s));
+  if (fused_put) {
+    const HaloPut hp = put_for(1);
+    HPCCG_TRY(launch_p_update(0, rk[0].m->n, rk[0].m->state, false, rk[0].x, rk[0].m->p, nullptr, &hp, s));
+  } else {
+    for (int q = 0; q < L; ++q) HPCCG_TRY(launch_waxpby(rk[q].m->n, 1.0, rk[q].x, 0.0, nullptr, rk[q].x, rk[q].m->p, nullptr, s));
+  }
   timers.tock();
-  HPCCG_TRY(do_exchange(false));
+  HPCCG_TRY(do_exchange(false, 1));
   timers.tick(T_SPMV);
   HPCCG_TRY(spmv_dot_all(FIN_STORE, 0, false, false));
   timers.tock();
+  // b is first read here: a host b may still be on its way (HPCCG() uploads it behind x, under the set-up SpMV)
+  if (io && io->b_ready) HPCCG_CUDA(cudaStreamWaitEvent(s, io->b_ready, 0));
   if (!unfused) {
     timers.tick(T_WAXPBY);
     for (int q = 0; q < L; ++q) {
@@ -1302,15 +1443,13 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     timers.tick(T_PUPD);
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
+      const HaloPut hp = fused_put ? put_for(k + 1) : HaloPut{};
+      const HaloPut *put = fused_put ? &hp : nullptr;
       if (k == 1) {
-        HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
+        if (put) HPCCG_TRY(launch_p_update(0, m->n, m->state, true, m->r, m->p, nullptr, put, s));
+        else HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
       } else if (defer_x) {
-        if (use_vec4(m->r, m->p, rk[q].x))
-          p_update_x_kernel<4><<<stream_grid((m->n + 3) / 4), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
-        else
-          p_update_x_kernel<2><<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->r, m->p, rk[q].x);
-        count_launch();
-        HPCCG_LAUNCH_CHECK();
+        HPCCG_TRY(launch_p_update(1, m->n, m->state, true, m->r, m->p, rk[q].x, put, s));
       } else {
         HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, &m->state->beta, m->p, m->p, m->state, s));
       }
@@ -1336,7 +1475,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       HPCCG_TRY(launch_spmv<true>(m, m->p, m->Ap, pb, pi.grid + pa.grid, total, fp, s));
       timers.tock();
     } else {
-      HPCCG_TRY(do_exchange(true));
+      HPCCG_TRY(do_exchange(true, k + 1));
       if (!unfused) {
         timers.tick(T_FUSED_SPMV);
         HPCCG_TRY(spmv_dot_all(FIN_PAP, k, true, true));
@@ -1396,7 +1535,27 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       if (*h_active == 0) break;
     }
   }
-  if (defer_x && max_iter > 1) {  // the x update of the last executed iteration
+  const bool stream_x_out = io && io->x_host && io->copy_stream && L == 1 && !capture_only;
+  if (!capture_only && stream_x_out) HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
+  if (stream_x_out) {
+    // final x to the host in chunks: chunk c is fixed up (the x update of the last executed iteration) on `s` and copied
+    // on copy_stream while chunk c+1 is being fixed up
+    hpccg_dev_matrix *m = rk[0].m;
+    const int chunks = hpccg_dev_matrix::kIoChunks;
+    const long long per = ((m->n + chunks - 1) / chunks + 511) / 512 * 512;  // 4 KiB-aligned chunk boundaries
+    int c = 0;
+    for (long long off = 0; off < m->n; off += per, ++c) {
+      const int len = (int)std::min<long long>(per, m->n - off);
+      if (defer_x && max_iter > 1) {
+        x_fixup_kernel<<<stream_grid((len + 1) / 2), kThreads, 0, s>>>(len, m->state, m->p + off, rk[0].x + off);
+        count_launch();
+        HPCCG_LAUNCH_CHECK();
+      }
+      HPCCG_CUDA(cudaEventRecord(m->ev_io[1 + c], s));
+      HPCCG_CUDA(cudaStreamWaitEvent(io->copy_stream, m->ev_io[1 + c], 0));
+      HPCCG_CUDA(cudaMemcpyAsync(io->x_host + off, rk[0].x + off, sizeof(double) * len, cudaMemcpyDeviceToHost, io->copy_stream));
+    }
+  } else if (defer_x && max_iter > 1) {  // the x update of the last executed iteration
     for (int q = 0; q < L; ++q) {
       hpccg_dev_matrix *m = rk[q].m;
       x_fixup_kernel<<<stream_grid((m->n + 1) / 2), kThreads, 0, s>>>(m->n, m->state, m->p, rk[q].x);
@@ -1405,11 +1564,12 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
     HPCCG_LAUNCH_CHECK();
   }
   if (capture_only) return 0;
-  HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
+  if (!stream_x_out) HPCCG_CUDA(cudaEventRecord(ev_loop1, s));
 
   // ---- results ----
   CgState hs;
   HPCCG_TRY(solve_readback(rk[0].m, max_iter, niters_out, normr_out, hist_host, &hs, s));
+  if (stream_x_out) HPCCG_CUDA(cudaStreamSynchronize(io->copy_stream));
   if (p2p) {
     int perr = 0;
     HPCCG_CUDA(cudaMemcpy(&perr, &link->error, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1442,22 +1602,31 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 
 }  // namespace hpccg
 
-extern "C" {
-
-int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters,
-                       double *normr, double *hist_host, double *times, double *loop_ms, int flags, void *stream) {
-  if (!m) return fail(HPCCG_ERR_ARG, "hpccg_dev_cg_solve: null matrix");
+namespace hpccg {
+int cg_solve_io(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters, double *normr,
+                double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t stream, const SolveIO *io) {
+  if (!m) return fail(HPCCG_ERR_ARG, "cg_solve: null matrix");
   const RankContext &c = ctx();
   std::vector<SolveRank> rk{{m, b, x, c.rank}};
   if (c.size > 1) {
     if (!nccl_ready() || nccl_size() != c.size || nccl_rank() != c.rank)
       return fail(HPCCG_ERR_STATE, "hpccg_dev_cg_solve: rank context is %d/%d but no matching NCCL communicator (hpccg_nccl_init)",
                   c.rank, c.size);
-    return cg_solve_impl(rk, c.size, true, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags,
-                         (cudaStream_t)stream);
+    return cg_solve_impl(rk, c.size, true, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, stream, false, io);
   }
-  if (!(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
-    return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+  return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, stream, false, io);
+}
+}  // namespace hpccg
+
+extern "C" {
+
+int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters,
+                       double *normr, double *hist_host, double *times, double *loop_ms, int flags, void *stream) {
+  if (!m) return fail(HPCCG_ERR_ARG, "hpccg_dev_cg_solve: null matrix");
+  const RankContext &c = ctx();
+  if (c.size > 1 || !(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
+    return cg_solve_io(m, b, x, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream, nullptr);
+  std::vector<SolveRank> rk{{m, b, x, c.rank}};
 
   // ---- CUDA-graph replay (launch-bound sizes): the launch sequence of a solve depends only on this key ----
   if (max_iter < 1) max_iter = 1;

@@ -46,6 +46,12 @@ struct hpccg_dev_matrix {
   int total_to_be_sent = 0;
   int *d_elements_to_send = nullptr;
   double *d_send_buffer = nullptr;
+  // inverse send maps for the put fused into the p-producing kernel (built by hpccg_dev_matrix_set_halo when every
+  // segment's rows lie in a compact range and no row is sent twice to one neighbour); link / dst are filled by
+  // peer_link_create
+  int *d_put_inv = nullptr;
+  hpccg::HaloPut put_plan{};
+  int put_fusable = 0;
 
   // workspace
   double *partials = nullptr;
@@ -59,6 +65,9 @@ struct hpccg_dev_matrix {
   long long scratch_cap = 0;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_p_ready = nullptr, ev_halo_done = nullptr;
+  // HPCCG() with host vectors: b arrives on comm_stream while the set-up SpMV runs; the final x leaves in chunks
+  static constexpr int kIoChunks = 8;
+  cudaEvent_t ev_io[kIoChunks + 2] = {};
 
   // CUDA-graph replay of a whole solve (HPCCG_SOLVE_GRAPH): the launch sequence is a function of this key only
   cudaGraphExec_t graph_exec = nullptr;
@@ -74,6 +83,7 @@ struct hpccg_dev_matrix {
   hpccg::PeerLink *peer_link = nullptr;   // device copy handed to the kernels
   std::vector<void *> ipc_opened;         // base pointers returned by cudaIpcOpenMemHandle
   int peer_tried = 0;
+  int generation = 0;                     // bumped whenever buffers a captured graph refers to are replaced
 };
 
 namespace hpccg {
@@ -88,6 +98,20 @@ const Device &device_info();
 int stream_grid(long long work_items, int blocks_per_sm = 8);
 
 int ensure_solver_workspace(hpccg_dev_matrix *m, int max_iter, int nranks);
+
+// Host-vector plumbing of HPCCG() (host_api.cu) threaded through the device loop so that copies overlap compute:
+//   b_ready : event after which the device copy of b is complete (the loop waits for it right before the first kernel
+//             that reads b, i.e. AFTER p = x and the set-up SpMV, HPCCG.cpp:347-352);
+//   x_host  : when set, the final x is produced chunk by chunk (x_fixup_kernel) and each chunk is copied to the host on
+//             copy_stream while the next one is computed; the call returns when the last chunk has landed.
+struct SolveIO {
+  cudaEvent_t b_ready = nullptr;
+  double *x_host = nullptr;
+  cudaStream_t copy_stream = nullptr;
+};
+// hpccg_dev_cg_solve without the graph-replay branch, with optional host-vector plumbing (single rank or one NCCL rank)
+int cg_solve_io(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters, double *normr,
+                double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t stream, const SolveIO *io);
 int ensure_scratch(hpccg_dev_matrix *m, long long doubles);
 
 }  // namespace hpccg

@@ -839,28 +839,51 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   const double *db = b;
   double *dx = x;
   if (!bd || !xd) HPCCG_TRY(ensure_scratch(m, std::max<long long>(m->npad, m->ncol + 2)));
-  if (!xd) {
-    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_x, x, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
-    dx = m->scratch_x;
-  }
-  if (!bd) {
-    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_y, b, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
-    db = m->scratch_y;
-  }
-  const int iters = std::max(max_iter, 1);
-  t_last_history.assign(iters, std::nan(""));
-  double local_times[16] = {0};
+  HPCCG_TRY(ensure_solver_workspace(m, std::max(max_iter, 1), ctx().size));
   // Per-kernel CUDA events cost ~6 API calls per iteration: irrelevant when a kernel runs for 100 us, but 3/4 of the wall
   // time of a launch-bound solve (20x30x10: 43 -> 12 us per iteration).  Below 2^20 rows a single-rank solve therefore
   // records only the loop time and splits it over times[1..3] by the kernels' algorithmic byte counts.
   const bool event_timers = ctx().size > 1 || m->n >= (1 << 20) || std::getenv("HPCCG_B200_TIMERS") != nullptr;
+  // Host vectors: the copies are ordered so that they overlap the solve where the algorithm allows it.  x goes first (p = x
+  // and Ap = A p need only x, HPCCG.cpp:347-349), b follows on the copy stream and is awaited right before r = b - Ap
+  // (:352); at the end x comes back in chunks behind the kernel that finishes it.  (The launch-bound graph path keeps the
+  // plain sequence: its copies are microseconds.)
+  SolveIO io;
+  const bool pipelined = event_timers && !std::getenv("HPCCG_B200_SERIAL_COPIES");
+  if (!xd) {
+    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_x, x, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
+    dx = m->scratch_x;
+    if (pipelined) io.x_host = x;
+  }
+  if (!bd) {
+    cudaStream_t bs = nullptr;
+    if (pipelined) {
+      bs = m->comm_stream;
+      cudaEvent_t x_up = m->ev_io[hpccg_dev_matrix::kIoChunks + 1];
+      HPCCG_CUDA(cudaEventRecord(x_up, nullptr));  // b shares the link with x: start it when x is through
+      HPCCG_CUDA(cudaStreamWaitEvent(bs, x_up, 0));
+    }
+    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_y, b, sizeof(double) * m->n, cudaMemcpyHostToDevice, bs));
+    db = m->scratch_y;
+    if (pipelined) {
+      HPCCG_CUDA(cudaEventRecord(m->ev_io[0], bs));
+      io.b_ready = m->ev_io[0];
+    }
+  }
+  io.copy_stream = m->comm_stream;
+  const int iters = std::max(max_iter, 1);
+  t_last_history.assign(iters, std::nan(""));
+  double local_times[16] = {0};
   int flags = event_timers ? HPCCG_SOLVE_TIMERS : HPCCG_SOLVE_GRAPH;  // launch-bound sizes: replay repeated solves as a graph
   if (const char *e = std::getenv("HPCCG_B200_UNFUSED"))
     if (e[0] == '1') flags |= HPCCG_SOLVE_UNFUSED;
   int it = 0;
   double nr = 0.0;
   double loop_ms = 0.0;
-  HPCCG_TRY(hpccg_dev_cg_solve(m, db, dx, max_iter, tolerance, &it, &nr, t_last_history.data(), local_times, &loop_ms, flags, nullptr));
+  if (pipelined)
+    HPCCG_TRY(cg_solve_io(m, db, dx, max_iter, tolerance, &it, &nr, t_last_history.data(), local_times, &loop_ms, flags, nullptr, &io));
+  else
+    HPCCG_TRY(hpccg_dev_cg_solve(m, db, dx, max_iter, tolerance, &it, &nr, t_last_history.data(), local_times, &loop_ms, flags, nullptr));
   if (!event_timers) {
     const double spmv_b = (m->format == 1 ? 2.0 : 12.0 * m->slots) + 16.0, ddot_b = 16.0 + 8.0, waxpby_b = 48.0 + 24.0;
     const double tot_b = spmv_b + ddot_b + waxpby_b, loop_s = loop_ms * 1e-3;
@@ -868,7 +891,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
     local_times[2] = loop_s * waxpby_b / tot_b;
     local_times[3] = loop_s * spmv_b / tot_b;
   }
-  if (!xd) HPCCG_CUDA(cudaMemcpy(x, dx, sizeof(double) * m->n, cudaMemcpyDeviceToHost));
+  if (!xd && !io.x_host) HPCCG_CUDA(cudaMemcpy(x, dx, sizeof(double) * m->n, cudaMemcpyDeviceToHost));
   niters = it;
   normr = nr;
 

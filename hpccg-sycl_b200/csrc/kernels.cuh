@@ -342,6 +342,7 @@ struct SpmvHalo {
   int n;               // local_nrow: columns >= n are halo entries (read with ld.global.cg, never through L1)
   int interior_begin;  // first row that references no halo column
   int interior_end;
+  int exch_idx;        // which exchange of this solve delivers the planes (exchange_stamp)
 };
 
 __device__ __forceinline__ void tma_prefetch_l2(const void *src_gmem, unsigned bytes) {
@@ -418,10 +419,10 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
     const int row = stage * kRows + tid;
     const bool touches_halo = halo.link && (stage * kRows < halo.interior_begin || (stage + 1) * kRows > halo.interior_end);
     if (touches_halo && !halo_ready) {
-      // the neighbours' planes for THIS exchange (stamp = the number the local halo_put_kernel just took) must have landed
+      // the neighbours' planes for THIS exchange (stamp = solve epoch | exchange index) must have landed
       if (tid < halo.link->nnb) {
         const Mailbox *own = halo.link->box[halo.link->rank];
-        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq))
+        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], exchange_stamp(halo.link->epoch, halo.exch_idx)))
           halo.link->error = 2;
       }
       __syncthreads();
@@ -517,7 +518,7 @@ spmv_pattern_kernel(const unsigned short *__restrict__ pat_id, const double *__r
     if (touches_halo && !halo_ready) {
       if (tid < halo.link->nnb) {
         const Mailbox *own = halo.link->box[halo.link->rank];
-        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], halo.link->halo_seq))
+        if (*reinterpret_cast<volatile int *>(&halo.link->error) != 0 || !peer_wait_ge(&own->halo_seq[tid], exchange_stamp(halo.link->epoch, halo.exch_idx)))
           halo.link->error = 2;
       }
       __syncthreads();
@@ -856,47 +857,141 @@ update_r_dot_kernel(int n, const double *alpha_dev, const double *__restrict__ A
   publish_and_finish(total, partials, blockIdx.x, total_partials, counter, fp, smem);
 }
 
-// x += alpha_{k-1} p_{k-1} (deferred HPCCG.cpp:383) ; p_k = r + beta p_{k-1} (HPCCG.cpp:369).  alpha, beta from the device state.
-template <int VEC>
+// ---- the kernel that produces p, with exchange_externals.cpp:103-112 folded in -----------------------------------------
+// MODE 1: x += alpha_{k-1} p_{k-1} (deferred HPCCG.cpp:383) ; p_k = r + beta p_{k-1} (HPCCG.cpp:369), alpha / beta from the
+//         device state.
+// MODE 0: p = src + 0.0 * src, the waxpby copies of HPCCG.cpp:347 (p = x) and :362 (p = r) with their arithmetic kept.
+// PUT: every row of p that a neighbour needs is also stored straight into that neighbour's halo tail over NVLink (inverse
+// send map, HaloPut).  The CTAs that own a tile of a segment's row range take a per-segment ticket when they are done; the
+// last one publishes the exchange stamp in the neighbour's mailbox (release, system scope) -- what the neighbour's SpMV
+// waits for at its halo-touching stages.  No separate put kernel, nothing of the exchange on the critical path.
+template <bool PUT>
+__device__ __forceinline__ bool put_elem(const HaloPut &put, long long e, double v) {
+  bool did = false;
+  if (PUT) {
+#pragma unroll
+    for (int s = 0; s < kMaxPeerNb; ++s)
+      if (s < put.nseg && e >= put.lo[s] && e < put.hi[s]) {
+        const int pos = __ldg(put.inv + put.inv_off[s] + (int)(e - put.lo[s]));
+        if (pos >= 0) {
+          put.dst[s][pos] = v;
+          did = true;
+        }
+      }
+  }
+  return did;
+}
+
+template <int VEC, int MODE, bool PUT>
 __global__ void __launch_bounds__(kThreads)
-p_update_x_kernel(int n, const CgState *st, const double *__restrict__ r, double *__restrict__ p, double *__restrict__ x) {
-  if (st->active == 0) return;
-  const double alpha = st->alpha, beta = st->beta;
-  const int nvec = n / VEC;
+p_update_x_kernel(int n, const CgState *st, int check_active, const double *__restrict__ r, double *__restrict__ p,
+                  double *__restrict__ x, const HaloPut put) {
+  if (check_active && st->active == 0) return;
+  double alpha = 0.0, beta = 0.0;
+  if (MODE == 1) {
+    alpha = st->alpha;
+    beta = st->beta;
+  }
+  bool did_put = false;
+  const int nvec = (n + VEC - 1) / VEC;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < nvec; i += gridDim.x * kThreads) {
     const long long e = (long long)VEC * i;
-    if (VEC == 4) {
+    bool near_seg = false;
+    if (PUT) {
+#pragma unroll
+      for (int s = 0; s < kMaxPeerNb; ++s) near_seg = near_seg || (s < put.nseg && e < put.hi[s] && e + VEC > put.lo[s]);
+    }
+    if (e + VEC > n) {  // tail (n not a multiple of VEC): scalar, same arithmetic
+      for (long long q = e; q < n; ++q) {
+        double pn;
+        if (MODE == 1) {
+          const double po = p[q];
+          x[q] = __dadd_rn(x[q], __dmul_rn(alpha, po));
+          pn = __dadd_rn(r[q], __dmul_rn(beta, po));
+        } else {
+          pn = __dadd_rn(r[q], __dmul_rn(0.0, r[q]));
+        }
+        p[q] = pn;
+        if (near_seg) did_put = put_elem<PUT>(put, q, pn) || did_put;
+      }
+    } else if (VEC == 4) {
       const double4v rv = ld_stream_f64x4(r + e);
-      double4v pv = ld_f64x4(p + e);
-      double4v xv = ld_f64x4(x + e);
-      xv.a = __dadd_rn(xv.a, __dmul_rn(alpha, pv.a));
-      xv.b = __dadd_rn(xv.b, __dmul_rn(alpha, pv.b));
-      xv.c = __dadd_rn(xv.c, __dmul_rn(alpha, pv.c));
-      xv.d = __dadd_rn(xv.d, __dmul_rn(alpha, pv.d));
-      pv.a = __dadd_rn(rv.a, __dmul_rn(beta, pv.a));
-      pv.b = __dadd_rn(rv.b, __dmul_rn(beta, pv.b));
-      pv.c = __dadd_rn(rv.c, __dmul_rn(beta, pv.c));
-      pv.d = __dadd_rn(rv.d, __dmul_rn(beta, pv.d));
-      st_f64x4(x + e, xv);
+      double4v pv;
+      if (MODE == 1) {
+        pv = ld_f64x4(p + e);
+        double4v xv = ld_f64x4(x + e);
+        xv.a = __dadd_rn(xv.a, __dmul_rn(alpha, pv.a));
+        xv.b = __dadd_rn(xv.b, __dmul_rn(alpha, pv.b));
+        xv.c = __dadd_rn(xv.c, __dmul_rn(alpha, pv.c));
+        xv.d = __dadd_rn(xv.d, __dmul_rn(alpha, pv.d));
+        pv.a = __dadd_rn(rv.a, __dmul_rn(beta, pv.a));
+        pv.b = __dadd_rn(rv.b, __dmul_rn(beta, pv.b));
+        pv.c = __dadd_rn(rv.c, __dmul_rn(beta, pv.c));
+        pv.d = __dadd_rn(rv.d, __dmul_rn(beta, pv.d));
+        st_f64x4(x + e, xv);
+      } else {
+        pv.a = __dadd_rn(rv.a, __dmul_rn(0.0, rv.a));
+        pv.b = __dadd_rn(rv.b, __dmul_rn(0.0, rv.b));
+        pv.c = __dadd_rn(rv.c, __dmul_rn(0.0, rv.c));
+        pv.d = __dadd_rn(rv.d, __dmul_rn(0.0, rv.d));
+      }
       st_f64x4(p + e, pv);
+      if (near_seg) {
+        did_put = put_elem<PUT>(put, e, pv.a) || did_put;
+        did_put = put_elem<PUT>(put, e + 1, pv.b) || did_put;
+        did_put = put_elem<PUT>(put, e + 2, pv.c) || did_put;
+        did_put = put_elem<PUT>(put, e + 3, pv.d) || did_put;
+      }
     } else {
       const double2 rv = ld_stream_f64x2(r + e);
-      double2 pv = *reinterpret_cast<const double2 *>(p + e);
-      double2 xv = *reinterpret_cast<const double2 *>(x + e);
-      xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
-      xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
-      pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
-      pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
-      *reinterpret_cast<double2 *>(x + e) = xv;
+      double2 pv;
+      if (MODE == 1) {
+        pv = *reinterpret_cast<const double2 *>(p + e);
+        double2 xv = *reinterpret_cast<const double2 *>(x + e);
+        xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
+        xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
+        pv.x = __dadd_rn(rv.x, __dmul_rn(beta, pv.x));
+        pv.y = __dadd_rn(rv.y, __dmul_rn(beta, pv.y));
+        *reinterpret_cast<double2 *>(x + e) = xv;
+      } else {
+        pv.x = __dadd_rn(rv.x, __dmul_rn(0.0, rv.x));
+        pv.y = __dadd_rn(rv.y, __dmul_rn(0.0, rv.y));
+      }
       *reinterpret_cast<double2 *>(p + e) = pv;
+      if (near_seg) {
+        did_put = put_elem<PUT>(put, e, pv.x) || did_put;
+        did_put = put_elem<PUT>(put, e + 1, pv.y) || did_put;
+      }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int i = nvec * VEC; i < n; ++i) {
-      const double po = p[i];
-      x[i] = __dadd_rn(x[i], __dmul_rn(alpha, po));
-      p[i] = __dadd_rn(r[i], __dmul_rn(beta, po));
+  if (PUT) {
+    if (did_put) __threadfence_system();  // my remote stores are visible system-wide before this CTA's ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int tile = kThreads * VEC, G = (int)gridDim.x, b = (int)blockIdx.x;
+      bool fenced = false;
+      for (int s = 0; s < put.nseg; ++s) {
+        // tiles [t0, t1] cover the segment's row range; tile t belongs to CTA t % G
+        int ctas = 1;
+        bool mine = (b == 0);  // an empty segment is still signalled (the neighbour waits for every stamp)
+        if (put.hi[s] > put.lo[s]) {
+          const int t0 = put.lo[s] / tile, cnt = (put.hi[s] - 1) / tile - t0 + 1;
+          ctas = cnt < G ? cnt : G;
+          mine = cnt >= G || ((b - t0 % G + G) % G) < cnt;
+        }
+        if (!mine) continue;
+        if (!fenced) {
+          __threadfence_system();
+          fenced = true;
+        }
+        const unsigned ticket = atomicInc(&put.link->put_ticket[s], (unsigned)(ctas - 1));  // wraps to 0 for the next exchange
+        if (ticket == (unsigned)(ctas - 1)) {
+          __threadfence_system();
+          st_release_sys(put.link->nb_flag[s], exchange_stamp(put.link->epoch, put.exch_idx));
+        }
+      }
     }
+  }
 }
 
 // After the loop: the x update of the last executed iteration (niters >= 1), HPCCG.cpp:383.
@@ -940,14 +1035,15 @@ halo_pack_kernel(int count, const int *__restrict__ elements_to_send, const doub
     send_buffer[i] = x[elements_to_send[i]];
 }
 
-// ---- exchange_externals.cpp:84-126 over peer memory -------------------------------------------------------------
+// ---- exchange_externals.cpp:84-126 over peer memory, stand-alone form ----------------------------------------------
+// (used when a send list has no compact inverse map; otherwise the put rides in p_update_x_kernel)
 // The gather of exchange_externals.cpp:103 and the MPI_Send of :110-112 in one kernel: element i of the send list is
 // stored straight into the neighbour's p vector (its halo tail) through the IPC-mapped pointer, i.e. across NVLink.
 // The block that takes the last ticket publishes the new exchange number in each neighbour's mailbox (release, system
 // scope), which is what the neighbour's SpMV waits for before it touches rows that reference halo columns.
 __global__ void __launch_bounds__(kThreads)
 halo_put_kernel(int count, const int *__restrict__ elements_to_send, const double *__restrict__ x, PeerLink *pl,
-                const CgState *st_check) {
+                const CgState *st_check, int exch_idx) {
   if (st_check && st_check->active == 0) return;
   __shared__ int s_last;
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < count; i += gridDim.x * kThreads) {
@@ -965,7 +1061,7 @@ halo_put_kernel(int count, const int *__restrict__ elements_to_send, const doubl
   if (!s_last) return;
   __threadfence_system();
   if (threadIdx.x == 0) {
-    const unsigned long long seq = ++pl->halo_seq;
+    const unsigned long long seq = exchange_stamp(pl->epoch, exch_idx);
     for (int i = 0; i < pl->nnb; ++i) st_release_sys(pl->nb_flag[i], seq);
   }
 }
@@ -1012,8 +1108,9 @@ __global__ void cg_scalar_kernel(const double *gathered, int nranks, FinishParam
   cg_finish(fp, g);
 }
 
-__global__ void cg_state_init_kernel(CgState *st) {
+__global__ void cg_state_init_kernel(CgState *st, PeerLink *link) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (link) link->epoch = link->epoch + 1;  // a new solve: its exchange stamps are above every earlier one
     st->rtrans = st->oldrtrans = st->alpha = st->neg_alpha = st->beta = st->pAp = st->normr = st->zero = st->local_sum = 0.0;
     st->niters = 0;
     st->active = 1;

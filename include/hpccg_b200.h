@@ -112,6 +112,12 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m);
 /* format: 0 = SELL-C values + int32 column ids (default, the north-star layout), 1 = pattern-coded. */
 int hpccg_dev_matrix_format(const hpccg_dev_matrix *m, int *format, int *patterns);
 
+/* Which data plane the multi-rank solves on this mirror use (decided collectively at the first solve):
+ * *peer = 1 when halos (exchange_externals.cpp:84-126) and scalar sums (ddot.cpp:77-82) travel through peer memory
+ * inside the kernels, 0 when they are NCCL send/recv + gathers between kernels (or the mirror never took part in a
+ * multi-rank solve); *fused_put = 1 when the halo put rides in the kernel that produces p (no exchange launch). */
+int hpccg_dev_matrix_comm(const hpccg_dev_matrix *m, int *peer, int *fused_put);
+
 /* ------------------------------------------------------------------------------------------------
  * Kernels (device pointers, asynchronous on `stream` = cudaStream_t or NULL)
  * ------------------------------------------------------------------------------------------------ */
