@@ -17,6 +17,7 @@
 #include "context.hpp"
 #include "device_matrix.hpp"
 #include "kernels.cuh"
+#include "pattern_march.cuh"
 
 namespace hpccg {
 
@@ -91,6 +92,8 @@ int stream_grid(long long work_items, int blocks_per_sm) {
 }
 
 static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+static bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31) == 0; }
 
 // A small per-device workspace for the stand-alone reductions (hpccg_dev_dot, max_abs_diff).
 struct GlobalWorkspace {
@@ -369,6 +372,60 @@ static int launch_pattern_t(const hpccg_dev_matrix *m, const double *x, double *
   return 0;
 }
 
+// ---- pattern-coded format, stencil-structured pattern 0: z-marching kernel (pattern_march.cuh) ---------------------
+// HPCCG_B200_PATTERN=classic keeps the one-gather-per-entry kernel (A/B).
+static bool use_march(const hpccg_dev_matrix *m, const double *x) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = std::getenv("HPCCG_B200_PATTERN");
+    mode = (e && std::string(e) == "classic") ? 0 : 1;
+  }
+  return mode == 1 && m->format == 1 && m->march.ok && aligned32(x);
+}
+
+template <int SLOTS, bool DOT, bool NEG1>
+static int march_ctas_per_sm() {
+  static PerDeviceInt cache;
+  int cached = cache.get();
+  if (cached) return cached;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_march_kernel<SLOTS, DOT, NEG1>, kThreads, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  cache.set(per_sm);
+  return per_sm;
+}
+
+template <int SLOTS, bool DOT, bool NEG1>
+static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y, long long x_len, int partial_offset,
+                          const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out) {
+  const MarchGeom &g = m->march;
+  const long long steps = (long long)g.cols_x * g.cols_y * g.nz;
+  const int grid = (int)std::min<long long>(steps, std::min(march_ctas_per_sm<SLOTS, DOT, NEG1>() * device_info().sm_count, kMaxPartials / 4));
+  if (grid_out) {
+    *grid_out = grid;
+    return 0;
+  }
+  spmv_pattern_march_kernel<SLOTS, DOT, NEG1><<<grid, kThreads, 0, s>>>(
+      m->pat_id, m->pat_mask, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, g, x, y, m->n, m->interior_begin,
+      m->interior_end, m->partials, partial_offset, grid, &m->state->counter, fp, halo);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+// whole-matrix launch (the marching kernel has no row-range form); grid_out != nullptr: only report the grid
+template <bool DOT>
+static int launch_march(const hpccg_dev_matrix *m, const double *x, double *y, long long x_len, int partial_offset,
+                        const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out = nullptr) {
+  const bool neg1 = m->march.neg1 != 0;
+  if (m->slots == 7)
+    return neg1 ? launch_march_t<7, DOT, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
+                : launch_march_t<7, DOT, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+  return neg1 ? launch_march_t<27, DOT, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
+              : launch_march_t<27, DOT, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+}
+
 #define HPCCG_PATTERN_DISPATCH(FN, DOT, ...)             \
   do {                                                   \
     if (m->slots == 7) return FN<7, DOT>(__VA_ARGS__);   \
@@ -391,8 +448,6 @@ static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, co
   return launch_spmv_reg<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
 }
 
-static bool aligned16(const void *p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
-static bool aligned32(const void *p) { return (reinterpret_cast<size_t>(p) & 31) == 0; }
 // 256-bit accesses in the loop's vector kernels unless HPCCG_B200_VEC=2 (A/B) or a caller's vector is only 16-byte aligned
 static bool use_vec4(const void *a, const void *b, const void *c) {
   static int mode = -1;
@@ -407,6 +462,12 @@ static bool use_vec4(const void *a, const void *b, const void *c) {
 static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool dot, const FinishParams &fp,
                      cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
   if (!aligned16(x) || !aligned16(y)) return fail(HPCCG_ERR_ARG, "SpMV vectors must be 16-byte aligned");
+  if (use_march(m, x) && aligned32(y)) {
+    // the 256-bit loads may start up to 3 elements before the last needed one: ncol % 4 == 0 keeps them inside ncol
+    // (checked when the geometry was accepted), the solver's own p is padded anyway
+    const long long x_len = (x == m->p) ? round_up(std::max(m->ncol, 2), 512) : m->ncol;
+    return dot ? launch_march<true>(m, x, y, x_len, 0, fp, s, halo) : launch_march<false>(m, x, y, x_len, 0, fp, s, halo);
+  }
   if (dot) {
     SpmvPlan pl = plan_spmv<true>(m, 0, m->n);
     return launch_spmv<true>(m, x, y, pl, 0, pl.grid, fp, s, halo);
@@ -790,6 +851,7 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->pat_val);
   cudaFree(m->pat_delta);
   cudaFree(m->pat_len);
+  cudaFree(m->pat_mask);
   cudaFree(m->d_elements_to_send);
   cudaFree(m->d_send_buffer);
   cudaFree(m->d_put_inv);
@@ -966,6 +1028,103 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
     return 0;
   }
 #undef HPCCG_CUDA_DROP
+  // Sub-pattern descriptors: pattern `id` = pattern 0 with some entries missing (same values, same deltas, same order).
+  // Boundary rows of a stencil are exactly that -- whole (sy, sz) lines and / or the x-1 / x+1 entries are absent -- and the
+  // marching SpMV runs them through the same unrolled code as interior rows: bits 0..8 = lines present, bit 9 = x-1 entries
+  // missing, bit 10 = x+1 entries missing.  Anything else (halo rows with remapped columns, perturbed rows, irregular
+  // sub-patterns) is marked generic and takes the per-row table path.
+  std::vector<unsigned> h_mask(npat, 0xFFFFFFFFu);
+  {
+    const bool s27 = m->slots == 27;
+    const int nruns = s27 ? 9 : 5;
+    auto run_first = [&](int k) { return s27 ? 3 * k : (k < 2 ? k : (k == 2 ? 2 : k + 2)); };
+    auto run_len = [&](int k) { return s27 ? 3 : (k == 2 ? 3 : 1); };
+    for (int id = 0; id < npat && h_len[0] == m->slots; ++id) {
+      unsigned mask = 0;
+      int j0 = 0;
+      bool sub = true;
+      for (int e = 0; e < h_len[id] && sub; ++e) {
+        const double v = h_val[(size_t)id * m->slots + e];
+        const int d = h_delta[(size_t)id * m->slots + e];
+        while (j0 < h_len[0] && !(h_delta[j0] == d && std::memcmp(&h_val[j0], &v, sizeof v) == 0)) ++j0;
+        if (j0 == h_len[0]) sub = false;
+        else mask |= 1u << j0++;
+      }
+      if (!sub) continue;
+      unsigned runs = 0;
+      int lm = -1, rm = -1;  // -1: no 3-line seen yet
+      bool regular = true;
+      for (int k = 0; k < nruns && regular; ++k) {
+        const int e0 = run_first(k);
+        const unsigned bits = (mask >> e0) & ((1u << run_len(k)) - 1u);
+        if (!bits) continue;
+        runs |= 1u << k;
+        if (run_len(k) == 3) {
+          const int l = (bits & 1u) ? 0 : 1, r = (bits & 4u) ? 0 : 1;
+          regular = (bits & 2u) != 0 && (lm < 0 || (lm == l && rm == r));
+          lm = l;
+          rm = r;
+        }
+      }
+      if (regular) h_mask[id] = runs | (lm == 1 ? (1u << 9) : 0u) | (rm == 1 ? (1u << 10) : 0u);
+    }
+  }
+  unsigned *pat_mask = nullptr;
+  {
+    cudaError_t e_ = cudaMalloc(&pat_mask, sizeof(unsigned) * npat);
+    if (e_ == cudaSuccess) e_ = cudaMemcpy(pat_mask, h_mask.data(), sizeof(unsigned) * npat, cudaMemcpyHostToDevice);
+    if (e_ != cudaSuccess) {
+      cudaFree(pat_mask);
+      drop();
+      return fail_cuda(e_, "pattern masks", __FILE__, __LINE__);
+    }
+  }
+  // Stencil structure of pattern 0, read off its own deltas: lines of (x-1, x, x+1) around centre deltas sy*nx + sz*nx*ny.
+  {
+    MarchGeom g{};
+    const int *d = h_delta.data();
+    const double *v = h_val.data();
+    bool ok = h_len[0] == m->slots;
+    int nx = 0;
+    long long plane = 0;
+    if (ok && m->slots == 27) {
+      for (int k = 0; k < 9 && ok; ++k) {
+        g.base[k] = d[3 * k + 1];
+        ok = d[3 * k] == g.base[k] - 1 && d[3 * k + 2] == g.base[k] + 1;
+      }
+      nx = g.base[5];
+      plane = g.base[7];
+      for (int sz = -1; sz <= 1 && ok; ++sz)
+        for (int sy = -1; sy <= 1; ++sy) ok = ok && g.base[3 * (sz + 1) + (sy + 1)] == sz * plane + sy * nx;
+      g.diag = 13;
+    } else if (ok && m->slots == 7) {
+      ok = d[2] == -1 && d[3] == 0 && d[4] == 1 && d[1] == -d[5] && d[0] == -d[6];
+      nx = d[5];
+      plane = d[6];
+      g.base[0] = d[0];
+      g.base[1] = d[1];
+      g.base[2] = 0;
+      g.base[3] = d[5];
+      g.base[4] = d[6];
+      g.diag = 3;
+    } else {
+      ok = false;
+    }
+    ok = ok && nx >= 16 && nx % 4 == 0 && plane > 0 && plane % nx == 0 && m->n % plane == 0 && m->ncol % 4 == 0;
+    if (ok) {
+      g.nx = nx;
+      g.ny = (int)(plane / nx);
+      g.nz = (int)(m->n / plane);
+      g.cols_x = (g.nx + kMarchWidth - 1) / kMarchWidth;
+      g.cols_y = (g.ny + kMarchLines - 1) / kMarchLines;
+      g.neg1 = 1;
+      for (int j = 0; j < m->slots; ++j)
+        if (j != g.diag && v[j] != -1.0) g.neg1 = 0;
+      g.ok = 1;
+    }
+    m->march = g;
+  }
+  m->pat_mask = pat_mask;
   std::memset(&m->pattern0, 0, sizeof m->pattern0);
   for (int j = 0; j < m->slots; ++j) {
     m->pattern0.value[j] = h_val[j];

@@ -7,6 +7,18 @@
 
 #include "cg_state.hpp"
 
+namespace hpccg {
+// geometry of a stencil-structured pattern 0 (pattern_march.cuh)
+struct MarchGeom {
+  int nx, ny, nz;      // rows are numbered ix + nx*iy + nx*ny*iz
+  int cols_x, cols_y;  // columns of 128 x 8 rows
+  int base[9];         // centre delta of each stencil line (27-pt: 9 lines of 3; 7-pt: 5 lines of 1,1,3,1,1)
+  int diag;            // entry index of the diagonal in pattern 0
+  int neg1;            // every other value of pattern 0 is -1.0
+  int ok;
+};
+}  // namespace hpccg
+
 // HBM layout of one rank's matrix and solver workspace:
 //   vals  : double [npad/128][slots][128]  SELL-C (C = 128, sigma = 1), slot j = j-th stored entry of the row
 //   cols  : int32  [npad/128][slots][128]  local column id, -1 = padding (masked, never multiplied)
@@ -35,6 +47,9 @@ struct hpccg_dev_matrix {
   int *pat_delta = nullptr;
   int *pat_len = nullptr;
   int npat = 0;
+  //   pat_mask  : uint32 [npat]          which entries of pattern 0 the pattern consists of (0xFFFFFFFF: not a sub-pattern)
+  unsigned *pat_mask = nullptr;
+  hpccg::MarchGeom march{};             // ok: pattern 0 is a 27- / 7-point stencil over x-fastest rows (z-marching SpMV)
   hpccg::Pattern0 pattern0;             // host copy of pattern 0, passed to the SpMV kernel as a __grid_constant__ parameter
 
   // rows [0,interior_begin) and [interior_end,n) may reference halo columns (>= n); rows in between do not

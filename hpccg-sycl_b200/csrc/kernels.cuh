@@ -810,6 +810,12 @@ __device__ __forceinline__ double4v ld_f64x4(const double *p) {
   asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p) : "memory");
   return v;
 }
+// read-only path, allocating in L1 (the gathered vector is meant to be re-read from L1)
+__device__ __forceinline__ double4v ld_f64x4_nc(const double *p) {
+  double4v v;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_f64x4(double *p, const double4v &v) {
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "d"(v.d) : "memory");
 }
