@@ -383,30 +383,41 @@ static bool use_march(const hpccg_dev_matrix *m, const double *x) {
   return mode == 1 && m->format == 1 && m->march.ok && aligned32(x);
 }
 
-template <int SLOTS, bool DOT, bool NEG1>
+// HPCCG_B200_MARCH_RING=1: keep the lines of the two older planes in a register ring instead of re-reading them from L1 (A/B:
+// 37 % instead of 61 % of the L1 wavefront peak, but 128 registers are not enough for ring + arithmetic: 1.08 vs 0.88 ms)
+static bool march_ring() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char *e = std::getenv("HPCCG_B200_MARCH_RING");
+    mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return mode == 1;
+}
+
+template <int SLOTS, bool DOT, bool NEG1, bool RING>
 static int march_ctas_per_sm() {
   static PerDeviceInt cache;
   int cached = cache.get();
   if (cached) return cached;
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_march_kernel<SLOTS, DOT, NEG1>, kThreads, 0) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_march_kernel<SLOTS, DOT, NEG1, RING>, kThreads, 0) != cudaSuccess ||
       per_sm < 1)
     per_sm = 1;
   cache.set(per_sm);
   return per_sm;
 }
 
-template <int SLOTS, bool DOT, bool NEG1>
+template <int SLOTS, bool DOT, bool NEG1, bool RING>
 static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y, long long x_len, int partial_offset,
                           const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out) {
   const MarchGeom &g = m->march;
   const long long steps = (long long)g.cols_x * g.cols_y * g.nz;
-  const int grid = (int)std::min<long long>(steps, std::min(march_ctas_per_sm<SLOTS, DOT, NEG1>() * device_info().sm_count, kMaxPartials / 4));
+  const int grid = (int)std::min<long long>(steps, std::min(march_ctas_per_sm<SLOTS, DOT, NEG1, RING>() * device_info().sm_count, kMaxPartials / 4));
   if (grid_out) {
     *grid_out = grid;
     return 0;
   }
-  spmv_pattern_march_kernel<SLOTS, DOT, NEG1><<<grid, kThreads, 0, s>>>(
+  spmv_pattern_march_kernel<SLOTS, DOT, NEG1, RING><<<grid, kThreads, 0, s>>>(
       m->pat_id, m->pat_mask, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, g, x, y, m->n, m->interior_begin,
       m->interior_end, m->partials, partial_offset, grid, &m->state->counter, fp, halo);
   count_launch();
@@ -420,10 +431,13 @@ static int launch_march(const hpccg_dev_matrix *m, const double *x, double *y, l
                         const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out = nullptr) {
   const bool neg1 = m->march.neg1 != 0;
   if (m->slots == 7)
-    return neg1 ? launch_march_t<7, DOT, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
-                : launch_march_t<7, DOT, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
-  return neg1 ? launch_march_t<27, DOT, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
-              : launch_march_t<27, DOT, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+    return neg1 ? launch_march_t<7, DOT, true, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
+                : launch_march_t<7, DOT, false, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+  if (march_ring())
+    return neg1 ? launch_march_t<27, DOT, true, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
+                : launch_march_t<27, DOT, false, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+  return neg1 ? launch_march_t<27, DOT, true, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
+              : launch_march_t<27, DOT, false, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
 }
 
 #define HPCCG_PATTERN_DISPATCH(FN, DOT, ...)             \
