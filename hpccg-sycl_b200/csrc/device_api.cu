@@ -472,6 +472,66 @@ static bool use_vec4(const void *a, const void *b, const void *c) {
   return mode == 4 && aligned32(a) && aligned32(b) && aligned32(c);
 }
 
+// HPCCG_B200_VEC_TMA="tile,stages" (doubles per tile, ring depth; "0" = plain 256-bit LDG/STG kernels): the loop's two vector
+// kernels stream through shared memory with cp.async.bulk (vec_stream_tma_kernel)
+struct VecTmaMode {
+  int tile = 0, stages = 0;
+};
+static const VecTmaMode &vec_tma() {
+  static VecTmaMode mode;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    mode.tile = 2048;
+    mode.stages = 3;
+    if (const char *e = std::getenv("HPCCG_B200_VEC_TMA")) {
+      int t = 0, st = 0;
+      const int got = std::sscanf(e, "%d,%d", &t, &st);
+      if (got >= 1) {
+        mode.tile = t;
+        mode.stages = got >= 2 ? st : 3;
+      }
+    }
+  }
+  return mode;
+}
+
+template <class OP, int TILE, int NSTAGES, bool PUT>
+static int launch_vec_tma_t(hpccg_dev_matrix *m, const VecPtrs &vp, const FinishParams &fp, const HaloPut *put, cudaStream_t s) {
+  using Cfg = VecTmaCfg<OP, TILE, NSTAGES>;
+  auto kern = vec_stream_tma_kernel<OP, TILE, NSTAGES, PUT>;
+  static PerDeviceInt cache;
+  int per_sm = cache.get();
+  if (!per_sm) {
+    HPCCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, Cfg::kSmemBytes) != cudaSuccess || per_sm < 1)
+      return fail(HPCCG_ERR_STATE, "TMA vector kernel cannot be resident (%d bytes of shared memory)", Cfg::kSmemBytes);
+    cache.set(per_sm);
+  }
+  const int grid = std::max(1, std::min(per_sm * device_info().sm_count, std::min(m->n / TILE, kMaxPartials)));
+  kern<<<grid, kThreads, Cfg::kSmemBytes, s>>>(m->n, m->state, vp, m->partials, grid, &m->state->counter, fp, put ? *put : HaloPut{});
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class OP>
+static int launch_vec_tma(hpccg_dev_matrix *m, const VecPtrs &vp, const FinishParams &fp, const HaloPut *put, cudaStream_t s) {
+  const VecTmaMode &v = vec_tma();
+#define HPCCG_VEC_CASE(T, S)                                                                        \
+  if (v.tile == T && v.stages == S && VecTmaCfg<OP, T, S>::kSmemBytes <= 227 * 1024)                \
+    return put ? launch_vec_tma_t<OP, T, S, true>(m, vp, fp, put, s) : launch_vec_tma_t<OP, T, S, false>(m, vp, fp, put, s);
+  HPCCG_VEC_CASE(1024, 2)
+  HPCCG_VEC_CASE(1024, 3)
+  HPCCG_VEC_CASE(1024, 4)
+  HPCCG_VEC_CASE(2048, 2)
+  HPCCG_VEC_CASE(2048, 3)
+  HPCCG_VEC_CASE(4096, 2)
+#undef HPCCG_VEC_CASE
+  // a shape this operation has no room for: the nearest that fits
+  return put ? launch_vec_tma_t<OP, 1024, 3, true>(m, vp, fp, put, s) : launch_vec_tma_t<OP, 1024, 3, false>(m, vp, fp, put, s);
+}
+
 // Whole-matrix SpMV (+ optional fused x.y) in one launch.
 static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool dot, const FinishParams &fp,
                      cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
@@ -1621,6 +1681,14 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
       if (k == 1) {
         if (put) HPCCG_TRY(launch_p_update(0, m->n, m->state, true, m->r, m->p, nullptr, put, s));
         else HPCCG_TRY(launch_waxpby(m->n, 1.0, m->r, 0.0, nullptr, m->r, m->p, m->state, s));
+      } else if (defer_x && vec_tma().tile > 0 && m->n >= (1 << 20) && aligned16(rk[q].x)) {
+        VecPtrs vp{};
+        vp.in[0] = m->r;
+        vp.in[1] = m->p;
+        vp.in[2] = rk[q].x;
+        vp.out[0] = m->p;
+        vp.out[1] = rk[q].x;
+        HPCCG_TRY(launch_vec_tma<VecOpPUpdate>(m, vp, FinishParams{}, put, s));
       } else if (defer_x) {
         HPCCG_TRY(launch_p_update(1, m->n, m->state, true, m->r, m->p, rk[q].x, put, s));
       } else {
@@ -1678,7 +1746,13 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
         hpccg_dev_matrix *m = rk[q].m;
         const bool v4 = defer_x && use_vec4(m->Ap, m->r, m->r);
         const int grid = stream_grid(v4 ? (m->n + 3) / 4 : (m->n + 1) / 2);
-        if (v4)
+        if (defer_x && vec_tma().tile > 0 && m->n >= (1 << 20)) {
+          VecPtrs vp{};
+          vp.in[0] = m->Ap;
+          vp.in[1] = m->r;
+          vp.out[0] = m->r;
+          HPCCG_TRY(launch_vec_tma<VecOpRUpdate>(m, vp, fp_for(FIN_RR, q, k, last, true), nullptr, s));
+        } else if (v4)
           update_r_dot_kernel<4><<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
                                                             fp_for(FIN_RR, q, k, last, true));
         else if (defer_x)
