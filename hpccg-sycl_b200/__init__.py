@@ -33,7 +33,7 @@ __all__ = [
     "yaml_report", "run_local_world", "launch_count", "dev",
 ]
 
-SOLVE_DEFAULT, SOLVE_UNFUSED, SOLVE_NO_OVERLAP, SOLVE_TIMERS, SOLVE_NCCL_ONLY, SOLVE_GRAPH, SOLVE_EAGER_X = 0, 1, 2, 4, 8, 16, 32
+SOLVE_DEFAULT, SOLVE_UNFUSED, SOLVE_NO_OVERLAP, SOLVE_TIMERS, SOLVE_NCCL_ONLY, SOLVE_GRAPH, SOLVE_EAGER_X, SOLVE_PERSISTENT = 0, 1, 2, 4, 8, 16, 32, 64
 
 
 def _ptr(v) -> int:

@@ -18,6 +18,7 @@
 #include "device_matrix.hpp"
 #include "kernels.cuh"
 #include "pattern_march.cuh"
+#include "persistent_cg.cuh"
 
 namespace hpccg {
 
@@ -926,6 +927,8 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->pat_delta);
   cudaFree(m->pat_len);
   cudaFree(m->pat_mask);
+  cudaFree(m->persist_win);
+
   cudaFree(m->d_elements_to_send);
   cudaFree(m->d_send_buffer);
   cudaFree(m->d_put_inv);
@@ -1211,6 +1214,7 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
   cudaFree(scal);
   cudaFree(rep);
   invalidate_graph(m);  // a captured solve replays the SELL kernels on the arrays released here
+  m->persist_state = -1;  // the single-kernel solve reads the SELL arrays
   cudaFree(m->vals);
   cudaFree(m->cols);
   m->vals = nullptr;
@@ -1850,6 +1854,120 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
 }  // namespace hpccg
 
 namespace hpccg {
+// ---- the whole solve as one kernel of one thread-block cluster (persistent_cg.cuh) -----------------------------------------
+template <int SLOTS>
+static int cluster_launch(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tol, cudaStream_t s, bool query_only,
+                          bool *fits) {
+  auto kern = cg_cluster_kernel<SLOTS>;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(m->persist_G);
+  cfg.blockDim = dim3(m->persist_threads);
+  cfg.dynamicSmemBytes = (size_t)m->persist_smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = m->persist_G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (query_only) {
+    *fits = false;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m->persist_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    *fits = clusters >= 1;
+    return 0;
+  }
+  const int *wlo = m->persist_win, *whi = m->persist_win + m->persist_G;
+  HPCCG_CUDA(cudaLaunchKernelEx(&cfg, kern, (const double *)m->vals, (const int *)m->cols, m->slots, m->n, m->persist_rows, m->persist_window, wlo, whi, b,
+                                x, max_iter, tol, m->state, m->hist));
+  count_launch();
+  return 0;
+}
+
+static int cluster_dispatch(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tol, cudaStream_t s, bool query_only,
+                            bool *fits) {
+  if (m->slots == 27) return cluster_launch<27>(m, b, x, max_iter, tol, s, query_only, fits);
+  if (m->slots == 7) return cluster_launch<7>(m, b, x, max_iter, tol, s, query_only, fits);
+  return cluster_launch<0>(m, b, x, max_iter, tol, s, query_only, fits);
+}
+
+static int persistent_prepare(hpccg_dev_matrix *m) {
+  if (m->persist_state != 0) return 0;
+  m->persist_state = -1;
+  if (m->format != 0 || m->ncol != m->n || !m->vals) return 0;
+  int dev = 0, max_smem = 0;
+  HPCCG_CUDA(cudaGetDevice(&dev));
+  HPCCG_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // as many CTAs as the cluster allows, one row per thread
+  const int G = std::min(kClusterMax, std::max(1, (m->n + 31) / 32));
+  const int rows = (m->n + G - 1) / G;
+  const int used = (m->n + rows - 1) / rows;  // CTAs that own rows
+  const int threads = (int)round_up(rows, 32);
+  if (threads > kClusterThreadsMax || (long long)m->slots * rows * 12 > max_smem) return 0;
+  int *win = nullptr;
+  HPCCG_CUDA(cudaMalloc(&win, sizeof(int) * 2 * used));
+  persist_window_kernel<<<used, kThreads>>>(m->cols, m->slots, m->n, rows, win, win + used);
+  count_launch();
+  std::vector<int> h(2 * used);
+  cudaError_t e = cudaMemcpy(h.data(), win, sizeof(int) * 2 * used, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    cudaFree(win);
+    return fail_cuda(e, "cluster solve plan", __FILE__, __LINE__);
+  }
+  int max_w = 0;
+  for (int b = 0; b < used; ++b) max_w = std::max(max_w, h[used + b] - h[b]);
+  const long long smem = (long long)rows * 16 + (long long)m->slots * rows * 8 + ((long long)m->slots * rows + 2) * 4 +
+                         (long long)(max_w + 2) * 16 + 64;
+  m->persist_window = (max_w + 1) & ~1;
+  m->persist_win = win;
+  m->persist_G = used;
+  m->persist_rows = rows;
+  m->persist_threads = threads;
+  m->persist_smem = (int)smem;
+  bool fits = false;
+  if (smem <= max_smem - 1024) HPCCG_TRY(cluster_dispatch(m, nullptr, nullptr, 0, 0.0, nullptr, true, &fits));
+  if (!fits) {  // the column reach of a row block does not fit, or no GPC can host the cluster: normal loop
+    cudaFree(win);
+    m->persist_win = nullptr;
+    return 0;
+  }
+  m->persist_state = 1;
+  return 0;
+}
+
+static int cg_solve_persistent(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tol, int *niters,
+                               double *normr, double *hist_host, double *loop_ms, cudaStream_t s) {
+  if (max_iter < 1) max_iter = 1;
+  HPCCG_TRY(ensure_solver_workspace(m, max_iter, 1));
+  HPCCG_CUDA(cudaMemsetAsync(m->hist, 0xFF, sizeof(double) * (max_iter + 1), s));  // NaN = "no iteration ran"
+  struct Ev {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Ev() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } ev;
+  HPCCG_CUDA(cudaEventCreate(&ev.a));
+  HPCCG_CUDA(cudaEventCreate(&ev.b));
+  HPCCG_CUDA(cudaEventRecord(ev.a, s));
+  HPCCG_TRY(cluster_dispatch(m, b, x, max_iter, tol, s, false, nullptr));
+  HPCCG_CUDA(cudaEventRecord(ev.b, s));
+  HPCCG_TRY(solve_readback(m, max_iter, niters, normr, hist_host, nullptr, s));
+  float ms = 0.f;
+  HPCCG_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+  if (loop_ms) *loop_ms = ms;
+  return 0;
+}
+
 int cg_solve_io(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters, double *normr,
                 double *hist_host, double *times, double *loop_ms, int flags, cudaStream_t stream, const SolveIO *io) {
   if (!m) return fail(HPCCG_ERR_ARG, "cg_solve: null matrix");
@@ -1871,6 +1989,10 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
                        double *normr, double *hist_host, double *times, double *loop_ms, int flags, void *stream) {
   if (!m) return fail(HPCCG_ERR_ARG, "hpccg_dev_cg_solve: null matrix");
   const RankContext &c = ctx();
+  if ((flags & HPCCG_SOLVE_PERSISTENT) && c.size == 1 && !(flags & (HPCCG_SOLVE_TIMERS | HPCCG_SOLVE_UNFUSED))) {
+    HPCCG_TRY(persistent_prepare(m));
+    if (m->persist_state == 1) return cg_solve_persistent(m, b, x, max_iter, tolerance, niters, normr, hist_host, loop_ms, (cudaStream_t)stream);
+  }
   if (c.size > 1 || !(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
     return cg_solve_io(m, b, x, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream, nullptr);
   std::vector<SolveRank> rk{{m, b, x, c.rank}};

@@ -92,6 +92,11 @@ struct hpccg_dev_matrix {
   int graph_max_iter = 0, graph_flags = 0;
   double graph_tol = 0.0;
 
+  // single-kernel solve for launch-bound sizes (persistent_cg.cuh): plan cached per matrix
+  int persist_state = 0;  // 0: not planned yet, 1: usable, -1: does not qualify
+  int persist_G = 0, persist_rows = 0, persist_threads = 0, persist_smem = 0, persist_window = 0;
+  int *persist_win = nullptr;            // [2][G] column windows
+
   // peer-memory link (multi-process runs on one NVSwitch domain): mailbox in this rank's HBM, IPC-mapped views of
   // the peers' mailboxes and of the neighbours' p vectors; peer_link == nullptr: NCCL send/recv + gathers are used
   hpccg::Mailbox *mailbox = nullptr;

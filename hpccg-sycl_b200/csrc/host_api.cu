@@ -874,7 +874,8 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   const int iters = std::max(max_iter, 1);
   t_last_history.assign(iters, std::nan(""));
   double local_times[16] = {0};
-  int flags = event_timers ? HPCCG_SOLVE_TIMERS : HPCCG_SOLVE_GRAPH;  // launch-bound sizes: replay repeated solves as a graph
+  // launch-bound sizes: the whole solve as one cooperative kernel where the matrix qualifies, else repeated solves replay as a graph
+  int flags = event_timers ? HPCCG_SOLVE_TIMERS : (HPCCG_SOLVE_GRAPH | (std::getenv("HPCCG_B200_NO_PERSISTENT") ? 0 : HPCCG_SOLVE_PERSISTENT));
   if (const char *e = std::getenv("HPCCG_B200_UNFUSED"))
     if (e[0] == '1') flags |= HPCCG_SOLVE_UNFUSED;
   int it = 0;

@@ -161,6 +161,10 @@ int hpccg_dev_max_abs_diff(int n, const double *v1, const double *v2, double *re
                                   * into a CUDA graph and replayed -- for launch-bound sizes; loop_ms then covers the whole solve */
 #define HPCCG_SOLVE_EAGER_X 32  /* x += alpha p in the kernel right after the SpMV (48 + 24 B/row) instead of deferred into the next
                                   * p-update (24 + 40 B/row, default); same arithmetic, kept for A/B measurements */
+#define HPCCG_SOLVE_PERSISTENT 64 /* single rank, launch-bound sizes (default format, up to ~9600 rows at 27 slots): the WHOLE solve is
+                                  * one kernel of one 16-CTA thread-block cluster -- matrix blocks resident in shared memory, partial
+                                  * sums and neighbouring r values exchanged through distributed shared memory, two cluster barriers
+                                  * per iteration; ignored (normal loop) when the matrix does not qualify; loop_ms = the whole solve */
 #define HPCCG_SOLVE_NCCL_ONLY 8 /* multi-GPU: NCCL send/recv + gathers between kernels instead of peer memory inside them */
 int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_iter, double tolerance, int *niters,
                        double *normr, double *hist_host, double *times, double *loop_ms, int flags, void *stream);

@@ -158,10 +158,71 @@ def test_solve_with_16_byte_aligned_vectors(H, refwrap, cuda):
     A.destroy()
 
 
-def test_graph_replay_of_repeated_solves_is_bit_identical(H, refwrap, cuda):
-    """HPCCG_SOLVE_GRAPH (what HPCCG() uses below 2^20 rows): the first solve with a key runs directly, the second is
-    captured into a CUDA graph, later ones replay it.  Same kernels, same grids, same reduction trees -> same bits."""
+@pytest.mark.parametrize("dims,stencil", [((20, 30, 10), 27), ((20, 30, 10), 7), ((10, 10, 10), 27), ((33, 17, 5), 27),
+                                           ((16, 16, 16), 27), ((1, 1, 1), 27), ((7, 1, 1), 27), ((40, 8, 3), 7)])
+def test_persistent_single_kernel_solve(H, refwrap, cuda, dims, stencil):
+    """HPCCG_SOLVE_PERSISTENT (what HPCCG() uses for launch-bound sizes): the whole solve is ONE kernel of one thread-block
+    cluster with the matrix blocks resident in shared memory and two cluster barriers per iteration.  Same bars as the
+    normal loop; repeated solves are bit-identical; the tolerance exit takes the reference's iteration count."""
     torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(stencil, True)
+    A = H.generate_matrix(*dims)
+    m = A.device()
+    n = A.local_nrow
+    b = torch.from_numpy(A.b.copy()).cuda()
+    with refwrap.RefWorld(*dims, stencil=stencil, variant=ref_variant()) as R:
+        ref = R.solve(150)
+        rt = R.solve(150, 1e-6)
+    launches = []
+    outs = []
+    for _ in range(2):
+        xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+        l0 = H.launch_count()
+        out = H.dev.cg_solve(m, b, xd, 150, 0.0, flags=H.SOLVE_PERSISTENT)
+        launches.append(H.launch_count() - l0)
+        check_history(out["hist"], ref["hist"], out["niters"], ref["niters"])
+        check_solution(xd.cpu().numpy(), ref["x"][0])
+        outs.append(out["hist"])
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    assert launches[1] == 1, launches  # one kernel for the whole solve
+    xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    out = H.dev.cg_solve(m, b, xd, 150, 1e-6, flags=H.SOLVE_PERSISTENT)
+    assert out["niters"] == rt["niters"]
+    if rt["normr"] >= 1e-10 * ref["hist"][0]:  # beyond that the recursion is rounding noise (check_history)
+        assert abs(out["normr"] - rt["normr"]) <= 1e-8 * rt["normr"]
+    out = H.dev.cg_solve(m, b, xd, 1, 0.0, flags=H.SOLVE_PERSISTENT)  # max_iter 1: set-up only (HPCCG.cpp:358)
+    assert out["niters"] == 0
+    # the reference-named call takes this path by itself below 2^20 rows
+    x = A.x.copy()
+    niters, normr, times, hist = H.HPCCG(A, A.b, x, 150, 0.0)
+    assert np.array_equal(hist[:niters + 1], outs[0][:niters + 1], equal_nan=True) and times[0] > 0
+    A.destroy()
+
+
+def test_persistent_solve_declines_what_does_not_fit(H, cuda):
+    """More rows than one cluster's shared memory holds: the flag is ignored and the normal loop runs (many launches)."""
+    torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(27, False)
+    A = H.generate_matrix(48, 48, 48)
+    m = A.device()
+    b = torch.from_numpy(A.b.copy()).cuda()
+    xd = torch.zeros(A.local_nrow, dtype=torch.float64, device="cuda")
+    l0 = H.launch_count()
+    out = H.dev.cg_solve(m, b, xd, 150, 0.0, flags=H.SOLVE_PERSISTENT)
+    assert out["niters"] == 149 and H.launch_count() - l0 > 100
+    assert (xd - 1.0).abs().max().item() <= 1e-12
+    H.set_options(27, True)
+    A.destroy()
+
+
+def test_graph_replay_of_repeated_solves_is_bit_identical(H, refwrap, cuda, monkeypatch):
+    """HPCCG_SOLVE_GRAPH (what HPCCG() uses below 2^20 rows when the single-kernel solve does not apply): the first solve
+    with a key runs directly, the second is captured into a CUDA graph, later ones replay it.  Same kernels, same grids,
+    same reduction trees -> same bits."""
+    torch = cuda
+    monkeypatch.setenv("HPCCG_B200_NO_PERSISTENT", "1")
     H.set_rank(0, 1)
     H.set_options(27, True)
     A = H.generate_matrix(20, 30, 10)
