@@ -7,6 +7,7 @@ constexpr int kThreads = 256;          // threads per block for every kernel her
 constexpr int kMaxPartials = 8192;     // capacity of the per-matrix block-partial array
 constexpr int kSliceRows = 128;        // C of the SELL-C layout: rows per slice
 constexpr int kRowPad = 512;           // local_nrow is padded to a multiple of this (4 slices)
+constexpr int kRaggedRows = 32;        // C of the ragged SELL-C-sigma mirror (format 2): one warp per slice
 
 // SELL-C (C = kSliceRows, sigma = 1: rows keep the reference's order) addressing of the matrix arrays:
 // slice s = row / C holds its `slots` x C entries contiguously, slot-major inside the slice, so that

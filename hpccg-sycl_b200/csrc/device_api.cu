@@ -160,10 +160,18 @@ int ensure_scratch(hpccg_dev_matrix *m, long long doubles) {
   return 0;
 }
 
-static int alloc_common(hpccg_dev_matrix *m) {
+static int alloc_common(hpccg_dev_matrix *m, long long elems = -1) {
   HPCCG_CUDA(cudaGetDevice(&m->device));
-  HPCCG_CUDA(cudaMalloc(&m->vals, sizeof(double) * (size_t)m->slots * m->npad));
-  HPCCG_CUDA(cudaMalloc(&m->cols, sizeof(int) * (size_t)m->slots * m->npad));
+  if (elems < 0) elems = (long long)m->slots * m->npad;
+  // memory guard: say what is missing instead of failing somewhere inside the repack
+  size_t free_b = 0, total_b = 0;
+  HPCCG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const double need = 12.0 * (double)elems + 64.0 * (double)m->npad;  // matrix + the solver's vectors
+  if (need > 0.97 * (double)free_b)
+    return fail(HPCCG_ERR_ALLOC, "device mirror needs %.1f GB (%lld stored slots of 12 bytes + vectors) but only %.1f GB are free",
+                need / 1e9, elems, (double)free_b / 1e9);
+  HPCCG_CUDA(cudaMalloc(&m->vals, sizeof(double) * (size_t)std::max<long long>(elems, 1)));
+  HPCCG_CUDA(cudaMalloc(&m->cols, sizeof(int) * (size_t)std::max<long long>(elems, 1)));
   HPCCG_CUDA(cudaMalloc(&m->partials, sizeof(double) * kMaxPartials));
   HPCCG_CUDA(cudaMalloc(&m->state, sizeof(CgState)));
   cg_state_init_kernel<<<1, 32>>>(m->state, nullptr);
@@ -447,8 +455,37 @@ static int launch_march(const hpccg_dev_matrix *m, const double *x, double *y, l
     return FN<27, DOT>(__VA_ARGS__);                     \
   } while (0)
 
+// ---- ragged SELL-C-sigma (format 2): one thread per row position ----------------------------------------------------------
+template <bool DOT>
+static SpmvPlan plan_ragged(const hpccg_dev_matrix *m, int row_begin, int row_end) {
+  SpmvPlan p{row_begin, row_end, 0, 0};
+  if (row_end <= row_begin) return p;
+  // with sigma-sorting a row lives anywhere in its window: whole-matrix launches only (the caller never splits then)
+  const int base = row_begin & ~(kRaggedRows - 1);
+  const int end = m->perm ? (int)m->npad : row_end;
+  p.tiles = (end - base + kThreads - 1) / kThreads;
+  p.grid = std::min(p.tiles, std::min(8 * device_info().sm_count, kMaxPartials / 4));
+  return p;
+}
+
+template <bool DOT>
+static int launch_ragged(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
+                         int total_partials, const FinishParams &fp, cudaStream_t s) {
+  if (pl.grid == 0) return 0;
+  if (m->perm && (pl.row_begin != 0 || pl.row_end != m->n))
+    return fail(HPCCG_ERR_STATE, "a sigma-sorted mirror has no contiguous row ranges");
+  const int pos_end = m->perm ? (int)m->npad : pl.row_end;
+  spmv_sell_ragged_kernel<DOT><<<pl.grid, kThreads, 0, s>>>(m->vals, m->cols, m->slice_slots, m->slice_off, m->perm, m->n, x, y,
+                                                            pl.row_begin, pos_end, m->partials, partial_offset, total_partials,
+                                                            &m->state->counter, fp);
+  count_launch();
+  HPCCG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <bool DOT>
 static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end) {
+  if (m->format == 2) return plan_ragged<DOT>(m, row_begin, row_end);
   if (m->format == 1) HPCCG_PATTERN_DISPATCH(plan_pattern, DOT, row_begin, row_end);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(plan_tma, DOT, row_begin, row_end);
   return plan_range<2>(row_begin, row_end, spmv_max_grid<DOT>(m->slots));
@@ -457,6 +494,10 @@ static SpmvPlan plan_spmv(const hpccg_dev_matrix *m, int row_begin, int row_end)
 template <bool DOT>
 static int launch_spmv(const hpccg_dev_matrix *m, const double *x, double *y, const SpmvPlan &pl, int partial_offset,
                        int total_partials, const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo = SpmvHalo{}) {
+  if (m->format == 2) {
+    if (halo.link) return fail(HPCCG_ERR_STATE, "peer-memory halo wait needs the TMA or pattern SpMV path");
+    return launch_ragged<DOT>(m, x, y, pl, partial_offset, total_partials, fp, s);
+  }
   if (m->format == 1) HPCCG_PATTERN_DISPATCH(launch_pattern_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (use_tma_path(m->slots)) HPCCG_TMA_DISPATCH(launch_tma_t, DOT, m, x, y, pl, partial_offset, total_partials, fp, s, halo);
   if (halo.link) return fail(HPCCG_ERR_STATE, "peer-memory halo wait needs the TMA SpMV path");
@@ -558,6 +599,97 @@ static FinishParams fin_store(double *out) {
   return fp;
 }
 
+// ---- ragged SELL-C-sigma mirror (format 2) from assembled host rows ----------------------------------------------------
+// HPCCG_B200_RAGGED=0 keeps the uniform-slot layout for every matrix (A/B); HPCCG_B200_SIGMA=<rows> sets the sorting window
+// (1 = no sorting).  Default 8192 rows = 256 slices: on a power-law matrix 1.15 x the stored entries (4096: 1.28 x, 1024: 1.56 x).
+static int ragged_sigma(bool has_halo) {
+  if (has_halo) return 1;  // halo-touching row RANGES must stay contiguous
+  int v = 8192;
+  if (const char *e = std::getenv("HPCCG_B200_SIGMA")) v = std::atoi(e);
+  return std::max(1, std::min(v, 1 << 24));
+}
+
+static int build_ragged(hpccg_dev_matrix *m, const int *nnz_in_row, const double *const *ptr_to_vals_in_row,
+                        const int *const *ptr_to_inds_in_row, unsigned nthreads) {
+  const int n = m->n;
+  const long long npos = m->npad, nslices = npos / kRaggedRows;
+  m->sigma = ragged_sigma(m->ncol > m->n);
+  // row of every position: identity, or -- per window of sigma rows -- rows by decreasing length (stable)
+  std::vector<int> perm(npos);
+  for (long long i = 0; i < npos; ++i) perm[i] = i < n ? (int)i : -1;
+  if (m->sigma > 1) {
+    const long long win = std::max<long long>(m->sigma, kRaggedRows);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        const long long nwin = (n + win - 1) / win;
+        for (long long w = nwin * t / nthreads; w < nwin * (t + 1) / nthreads; ++w) {
+          const long long lo = w * win, hi = std::min<long long>(n, lo + win);
+          std::stable_sort(perm.begin() + lo, perm.begin() + hi, [&](int a, int b) { return nnz_in_row[a] > nnz_in_row[b]; });
+        }
+      });
+    for (auto &t : th) t.join();
+  }
+  std::vector<int> slots(nslices, 0);
+  std::vector<long long> off(nslices + 1, 0);
+  for (long long sl = 0; sl < nslices; ++sl) {
+    int mx = 0;
+    for (int l = 0; l < kRaggedRows; ++l) {
+      const int row = perm[sl * kRaggedRows + l];
+      if (row >= 0) mx = std::max(mx, nnz_in_row[row]);
+    }
+    slots[sl] = mx;
+    off[sl + 1] = off[sl] + (long long)mx * kRaggedRows;
+  }
+  m->total_elems = off[nslices];
+  HPCCG_TRY(alloc_common(m, m->total_elems));
+  HPCCG_CUDA(cudaMalloc(&m->slice_slots, sizeof(int) * nslices));
+  HPCCG_CUDA(cudaMalloc(&m->slice_off, sizeof(long long) * (nslices + 1)));
+  HPCCG_CUDA(cudaMemcpy(m->slice_slots, slots.data(), sizeof(int) * nslices, cudaMemcpyHostToDevice));
+  HPCCG_CUDA(cudaMemcpy(m->slice_off, off.data(), sizeof(long long) * (nslices + 1), cudaMemcpyHostToDevice));
+  if (m->sigma > 1) {
+    HPCCG_CUDA(cudaMalloc(&m->perm, sizeof(int) * npos));
+    HPCCG_CUDA(cudaMemcpy(m->perm, perm.data(), sizeof(int) * npos, cudaMemcpyHostToDevice));
+  }
+  // repack through one staging buffer per array, runs of whole slices at a time (a run is contiguous on the device)
+  long long cap = 1 << 22;
+  for (long long sl = 0; sl < nslices; ++sl) cap = std::max(cap, off[sl + 1] - off[sl]);
+  std::vector<double> sv(cap);
+  std::vector<int> sc(cap);
+  long long s0 = 0;
+  while (s0 < nslices) {
+    long long s1 = s0 + 1;
+    while (s1 < nslices && off[s1 + 1] - off[s0] <= cap) ++s1;
+    const long long e0 = off[s0], cnt = off[s1] - e0;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        for (long long sl = s0 + (s1 - s0) * t / nthreads; sl < s0 + (s1 - s0) * (t + 1) / nthreads; ++sl)
+          for (int l = 0; l < kRaggedRows; ++l) {
+            const int row = perm[sl * kRaggedRows + l];
+            const int nnz = row >= 0 ? nnz_in_row[row] : 0;
+            const long long base = off[sl] - e0 + l;
+            for (int j = 0; j < nnz; ++j) {
+              sv[base + (long long)j * kRaggedRows] = ptr_to_vals_in_row[row][j];
+              sc[base + (long long)j * kRaggedRows] = ptr_to_inds_in_row[row][j];
+            }
+            for (int j = nnz; j < slots[sl]; ++j) {
+              sv[base + (long long)j * kRaggedRows] = 0.0;
+              sc[base + (long long)j * kRaggedRows] = -1;
+            }
+          }
+      });
+    for (auto &t : th) t.join();
+    if (cnt > 0) {
+      HPCCG_CUDA(cudaMemcpy(m->vals + e0, sv.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice));
+      HPCCG_CUDA(cudaMemcpy(m->cols + e0, sc.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice));
+    }
+    s0 = s1;
+  }
+  m->format = 2;
+  return 0;
+}
+
 }  // namespace hpccg
 
 using namespace hpccg;
@@ -624,6 +756,7 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
   // slot count = longest row; first/last rows that touch halo columns bound the interior range
   const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
   std::vector<int> tmax(nthreads, 0), tfirst(nthreads, n), tlast(nthreads, -1), tbad(nthreads, 0);
+  std::vector<long long> tsum(nthreads, 0);
   {
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nthreads; ++t)
@@ -632,6 +765,7 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
         for (long long i = lo; i < hi; ++i) {
           const int nnz = nnz_in_row[i];
           if (nnz > tmax[t]) tmax[t] = nnz;
+          tsum[t] += nnz;
           const int *ci = ptr_to_inds_in_row[i];
           for (int j = 0; j < nnz; ++j) {
             if (ci[j] < 0 || ci[j] >= local_ncol) tbad[t] = 1;
@@ -646,9 +780,11 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
   }
   int slots = 1;
   bool bad = false;
+  long long stored = 0;
   for (unsigned t = 0; t < nthreads; ++t) {
     slots = std::max(slots, tmax[t]);
     bad = bad || tbad[t];
+    stored += tsum[t];
   }
   if (bad) return fail(HPCCG_ERR_ARG, "hpccg_dev_matrix_create: column index outside [0, local_ncol) -- run make_local_matrix first");
 
@@ -691,6 +827,24 @@ int hpccg_dev_matrix_create(int local_nrow, int local_ncol, const int *nnz_in_ro
   }
   m->interior_begin = a;
   m->interior_end = std::max(a, b);
+
+  // Rows of different lengths (file matrices, thin blocks): SELL-C-sigma proper -- per-slice slot counts, rows sorted by
+  // length inside windows of sigma rows -- instead of padding every row to the longest one, when that padding would exceed
+  // 10 % of the stored entries.  The 27- / 7-slot stencil matrices keep the uniform layout: that is what the TMA kernels and
+  // the pattern encoder read, and their padding is 0.6 %.
+  {
+    const char *e = std::getenv("HPCCG_B200_RAGGED");
+    const bool want = e ? e[0] == '1' : (slots != 27 && slots != 7 && 10 * stored < 9 * (long long)slots * n);
+    if (want && !(e && e[0] == '0')) {
+      int rc = build_ragged(m, nnz_in_row, ptr_to_vals_in_row, ptr_to_inds_in_row, nthreads);
+      if (rc) {
+        hpccg_dev_matrix_destroy(m);
+        return rc;
+      }
+      *out = m;
+      return 0;
+    }
+  }
 
   int rc = alloc_common(m);
   if (rc) {
@@ -927,6 +1081,9 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->pat_delta);
   cudaFree(m->pat_len);
   cudaFree(m->pat_mask);
+  cudaFree(m->slice_slots);
+  cudaFree(m->slice_off);
+  cudaFree(m->perm);
   cudaFree(m->persist_win);
 
   cudaFree(m->d_elements_to_send);
@@ -967,6 +1124,35 @@ int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int 
   // The device arrays are SELL-C (or pattern-coded); the caller receives the canonical column-major
   // [slots][padded_rows] view with the original values and column ids.
   const size_t total = (size_t)m->slots * m->npad;
+  if (m->format == 2) {
+    const long long nslices = m->npad / kRaggedRows;
+    std::vector<double> tv(vals_host ? m->total_elems : 0);
+    std::vector<int> tc(m->total_elems), sl(nslices), pm(m->npad);
+    std::vector<long long> of(nslices + 1);
+    if (vals_host && m->total_elems) HPCCG_CUDA(cudaMemcpy(tv.data(), m->vals, sizeof(double) * m->total_elems, cudaMemcpyDeviceToHost));
+    if (m->total_elems) HPCCG_CUDA(cudaMemcpy(tc.data(), m->cols, sizeof(int) * m->total_elems, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(sl.data(), m->slice_slots, sizeof(int) * nslices, cudaMemcpyDeviceToHost));
+    HPCCG_CUDA(cudaMemcpy(of.data(), m->slice_off, sizeof(long long) * (nslices + 1), cudaMemcpyDeviceToHost));
+    if (m->perm) HPCCG_CUDA(cudaMemcpy(pm.data(), m->perm, sizeof(int) * m->npad, cudaMemcpyDeviceToHost));
+    else
+      for (long long i = 0; i < m->npad; ++i) pm[i] = (int)i;
+    for (size_t i = 0; i < total; ++i) {
+      if (vals_host) vals_host[i] = 0.0;
+      if (cols_host) cols_host[i] = -1;
+    }
+    for (long long pos = 0; pos < m->npad; ++pos) {
+      const int row = pm[pos];
+      if (row < 0 || row >= m->npad) continue;
+      const long long s_ = pos / kRaggedRows, l = pos % kRaggedRows;
+      for (int j = 0; j < sl[s_]; ++j) {
+        const long long o = of[s_] + (long long)j * kRaggedRows + l;
+        if (tc[o] < 0) continue;
+        if (vals_host) vals_host[(size_t)j * m->npad + row] = tv[o];
+        if (cols_host) cols_host[(size_t)j * m->npad + row] = tc[o];
+      }
+    }
+    return 0;
+  }
   if (m->format == 0) {
     std::vector<double> tv(vals_host ? total : 0);
     std::vector<int> tc(cols_host ? total : 0);
@@ -1000,6 +1186,7 @@ int hpccg_dev_matrix_download(const hpccg_dev_matrix *m, double *vals_host, int 
 int hpccg_dev_matrix_bytes(const hpccg_dev_matrix *m, long long *bytes) {
   if (!m || !bytes) return fail(HPCCG_ERR_ARG, "null argument");
   if (m->format == 0) *bytes = (long long)m->slots * m->npad * 12;
+  else if (m->format == 2) *bytes = m->total_elems * 12 + (m->npad / kRaggedRows) * 12 + (m->perm ? 4 * m->npad : 0);
   else *bytes = 2LL * m->npad + (long long)m->npat * (m->slots * 12 + 4);
   return 0;
 }
@@ -1024,7 +1211,7 @@ int hpccg_dev_matrix_comm(const hpccg_dev_matrix *m, int *peer, int *fused_put) 
 // left in format 0; that is not an error.
 int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
   if (!m) return fail(HPCCG_ERR_ARG, "null matrix");
-  if (m->format == 1 || (m->slots != 27 && m->slots != 7) || m->slots > kPatternSlots) return 0;
+  if (m->format != 0 || (m->slots != 27 && m->slots != 7) || m->slots > kPatternSlots) return 0;
   const unsigned table_size = 1u << 21, mask = table_size - 1;
   unsigned long long *keys = nullptr, *freq = nullptr;
   int *ids = nullptr, *scal = nullptr, *rep = nullptr, *pat_delta = nullptr, *pat_len = nullptr;
@@ -1505,7 +1692,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
   // TMA kernel, or it is pattern-coded -- travels inside the exchange as an eligibility bit and all ranks take one decision.
   PeerLink *link = nullptr;
   if (nccl && !(flags & HPCCG_SOLVE_NCCL_ONLY)) {
-    const bool eligible = use_tma_path(rk[0].m->slots) || rk[0].m->format == 1;
+    const bool eligible = rk[0].m->format == 1 || (rk[0].m->format == 0 && use_tma_path(rk[0].m->slots));
     HPCCG_TRY(peer_link_create(rk[0].m, eligible));
     link = rk[0].m->peer_link;
   }
@@ -1756,6 +1943,7 @@ static int cg_solve_impl(std::vector<SolveRank> &rk, int R, bool nccl, int max_i
           vp.in[1] = m->r;
           vp.out[0] = m->r;
           HPCCG_TRY(launch_vec_tma<VecOpRUpdate>(m, vp, fp_for(FIN_RR, q, k, last, true), nullptr, s));
+          continue;  // (counted by the launcher)
         } else if (v4)
           update_r_dot_kernel<4><<<grid, kThreads, 0, s>>>(m->n, &m->state->alpha, m->Ap, m->r, m->partials, grid, &m->state->counter,
                                                             fp_for(FIN_RR, q, k, last, true));

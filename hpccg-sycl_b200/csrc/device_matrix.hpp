@@ -52,6 +52,17 @@ struct hpccg_dev_matrix {
   hpccg::MarchGeom march{};             // ok: pattern 0 is a 27- / 7-point stencil over x-fastest rows (z-marching SpMV)
   hpccg::Pattern0 pattern0;             // host copy of pattern 0, passed to the SpMV kernel as a __grid_constant__ parameter
 
+  // format 2 (SELL-C-sigma proper, for matrices whose rows differ in length -- read_HPC_row.cpp:217-373 feeds arbitrary rows):
+  //   slice s (kRaggedRows = 32 row POSITIONS, one warp) stores slice_slots[s] = its longest row's length slots, slot-major, at
+  //   element offset slice_off[s] of vals / cols; total_elems = slice_off[nslices].  With sigma > 1 the rows of every window
+  //   of sigma rows are sorted by decreasing length before they are dealt to slices (less padding); perm[position] =
+  //   original row, y is stored through it.  sigma = 1 (no perm) wherever row RANGES must stay contiguous (halo ranges).
+  int *slice_slots = nullptr;
+  long long *slice_off = nullptr;
+  int *perm = nullptr;
+  long long total_elems = 0;
+  int sigma = 1;
+
   // rows [0,interior_begin) and [interior_end,n) may reference halo columns (>= n); rows in between do not
   int interior_begin = 0, interior_end = 0;
 

@@ -325,8 +325,23 @@ int reduce_across_ranks(double *value, bool take_max) {
   const RankContext &c = ctx();
   if (c.size == 1) return 0;
   if (!nccl_ready()) return fail(HPCCG_ERR_STATE, "rank context has %d ranks but no NCCL communicator", c.size);
-  double *d = nullptr;
-  HPCCG_CUDA(cudaMalloc(&d, sizeof(double) * c.size));
+  // one small gather buffer per rank thread, kept (a multi-rank ddot used to cudaMalloc / cudaFree on every call)
+  struct Gather {
+    double *d = nullptr;
+    int cap = 0;
+    ~Gather() {
+      if (d) cudaFree(d);
+    }
+  };
+  static thread_local Gather gather;
+  if (gather.cap < c.size) {
+    if (gather.d) cudaFree(gather.d);
+    gather.d = nullptr;
+    gather.cap = 0;
+    HPCCG_CUDA(cudaMalloc(&gather.d, sizeof(double) * std::max(c.size, 16)));
+    gather.cap = std::max(c.size, 16);
+  }
+  double *d = gather.d;
   HPCCG_CUDA(cudaMemcpy(d + c.rank, value, sizeof(double), cudaMemcpyHostToDevice));
   int rc = nccl_allgather_double(d, nullptr);
   std::vector<double> all(c.size);
@@ -334,7 +349,6 @@ int reduce_across_ranks(double *value, bool take_max) {
     cudaError_t e = cudaMemcpy(all.data(), d, sizeof(double) * c.size, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail_cuda(e, "gather copy", __FILE__, __LINE__);
   }
-  cudaFree(d);
   if (rc) return rc;
   double g = all[0];
   for (int r = 1; r < c.size; ++r) g = take_max ? std::max(g, all[r]) : g + all[r];

@@ -295,6 +295,58 @@ spmv_ell_kernel(const double *__restrict__ vals, const int *__restrict__ cols, l
   }
 }
 
+// ---- HPC_sparsemv.cpp:68-89 on the ragged SELL-C-sigma mirror (format 2) --------------------------------------------------
+// One thread per row position, one warp per slice: a slice (kRaggedRows = 32 positions) has its own slot count and element
+// offset, so a matrix with a few long rows pads only the slices those rows fall into (C = 32 instead of the uniform layout's
+// 128 because a power-law tail needs it: 1.3 x the stored entries instead of 3.5 x on the test matrix).  Entries are summed in stored order (padding slots carry column -1
+// and are skipped), i.e. the result of a row is bit-identical to every other path; with sigma-sorting the row of a position
+// is perm[position].  Positions [pos_begin, pos_end) are processed (contiguous row ranges need sigma = 1).
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_sell_ragged_kernel(const double *__restrict__ vals, const int *__restrict__ cols, const int *__restrict__ slice_slots,
+                        const long long *__restrict__ slice_off, const int *__restrict__ perm, int n,
+                        const double *__restrict__ x, double *__restrict__ y, int pos_begin, int pos_end, double *partials,
+                        int partial_offset, int total_partials, unsigned *counter, FinishParams fp) {
+  __shared__ double smem[kThreads / 32];
+  if (fp.check_active && fp.st->active == 0) return;
+  double dot = 0.0;
+  const int base = pos_begin & ~(kRaggedRows - 1);
+  for (long long pos = base + (long long)blockIdx.x * kThreads + threadIdx.x; pos < pos_end; pos += (long long)gridDim.x * kThreads) {
+    if (pos < pos_begin) continue;
+    const int slice = (int)(pos / kRaggedRows), l = (int)(pos % kRaggedRows);
+    const int ns = __ldg(slice_slots + slice);
+    const long long off = __ldg(slice_off + slice) + l;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + 4 <= ns; j += 4) {  // four entries' loads in flight, summed in order
+      int c[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = ld_stream_s32(cols + off + (long long)(j + u) * kRaggedRows);
+        v[u] = ld_stream_f64(vals + off + (long long)(j + u) * kRaggedRows);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c[u] >= 0) sum = __dadd_rn(sum, __dmul_rn(v[u], __ldg(x + c[u])));
+    }
+    for (; j < ns; ++j) {
+      const int c = ld_stream_s32(cols + off + (long long)j * kRaggedRows);
+      const double v = ld_stream_f64(vals + off + (long long)j * kRaggedRows);
+      if (c >= 0) sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+    }
+    const int row = perm ? __ldg(perm + pos) : (int)pos;
+    if (row >= 0 && row < n) {
+      y[row] = sum;
+      if (DOT) dot = __dadd_rn(dot, __dmul_rn(__ldg(x + row), sum));
+    }
+  }
+  if (DOT) {
+    const double total = block_sum(dot, smem);
+    publish_and_finish(total, partials, partial_offset + blockIdx.x, total_partials, counter, fp, smem);
+  }
+}
+
 // ---- HPC_sparsemv.cpp:68-89, TMA path: the main SpMV --------------------------------------------------------
 // One stage = SPS consecutive slices = one contiguous block of the vals array and one of the cols array,
 // fetched by a single elected thread with two cp.async.bulk (global -> shared, mbarrier complete_tx) and an L2

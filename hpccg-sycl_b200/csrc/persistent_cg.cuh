@@ -91,7 +91,7 @@ cg_cluster_kernel(const double *__restrict__ vals, const int *__restrict__ cols,
                   double *__restrict__ x, int max_iter, double tol, CgState *st, double *hist) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[32];
   __shared__ double mail[2][kClusterMax];
   const int slots = SLOTS > 0 ? SLOTS : slots_rt;

@@ -17,6 +17,26 @@ GOLDEN = Path(__file__).parent / "golden"
 REL_HIST = 1e-8
 
 
+def reference_self_spread(dims, stencil=27, max_iter=150):
+    """how far the reference is from ITSELF once the residual has dropped ten decades -- its serial build
+    against its OpenMP build on the same problem (None when oracle/_ref has only one of them).  Returns (first iteration of
+    the noise regime, largest relative difference inside the regular regime, largest decade distance beyond it)."""
+    import refwrap
+    if not (refwrap.available("serial") and refwrap.available("omp")):
+        return None
+    with refwrap.RefWorld(*dims, stencil=stencil, variant="serial") as R:
+        a = R.solve(max_iter)["hist"]
+    with refwrap.RefWorld(*dims, stencil=stencil, variant="omp") as R:
+        b = R.solve(max_iter)["hist"]
+    ran = ~np.isnan(a) & ~np.isnan(b) & (a > 0) & (b > 0)
+    regular = ran & (a >= 1e-10 * a[0])
+    noisy = ran & ~regular
+    rel = float((np.abs(a[regular] - b[regular]) / a[regular]).max())
+    decades = float(np.abs(np.log10(a[noisy] / b[noisy])).max()) if noisy.any() else 0.0
+    first = int(np.argmax(noisy)) if noisy.any() else -1
+    return first, rel, decades
+
+
 def check_history(hist, ref_hist, niters, ref_niters):
     """Regular regime (normr_k >= 1e-10 normr_0): <= 1e-8 relative, every iteration.  Beyond it the recursion is
     rounding noise -- the reference's own serial / OpenMP / 3-thread builds are decades apart there (SURVEY.md 4.1;
@@ -67,6 +87,32 @@ def test_hpccg_matches_reference(H, refwrap, cuda, dims, stencil):
     assert normr == hist[niters]
     check_solution(x, ref["x"][0])
     assert times[0] > 0 and times[3] > 0
+    A.destroy()
+
+
+def test_noise_regime_relaxation_is_evidenced(H, refwrap, cuda, capsys):
+    """The relaxed bar of check_history beyond ten decades is not an assertion of convenience: the reference's own serial
+    and OpenMP builds agree to <= 1e-8 inside the regular regime and drift apart by DECADES beyond it, on the very problem
+    where the first B200 run was 2.9 decades from the serial reference (10^3).  The spread is printed next to ours."""
+    spread = reference_self_spread((10, 10, 10))
+    if spread is None:
+        pytest.skip("needs the serial and the OpenMP build of the reference (oracle/_ref)")
+    first, rel, decades = spread
+    H.set_rank(0, 1)
+    H.set_options(27, True)
+    A = H.generate_matrix(10, 10, 10)
+    x = A.x.copy()
+    niters, normr, _, hist = H.HPCCG(A, A.b, x, 150, 0.0)
+    with refwrap.RefWorld(10, 10, 10, variant="serial") as R:
+        ref = R.solve(150)["hist"]
+    ran = ~np.isnan(hist) & ~np.isnan(ref) & (hist > 0) & (ref > 0)
+    noisy = ran & (ref < 1e-10 * ref[0])
+    ours = float(np.abs(np.log10(hist[noisy] / ref[noisy])).max()) if noisy.any() else 0.0
+    with capsys.disabled():
+        print(f"\n[noise regime, 10x10x10] starts at iteration {first}; reference serial vs OpenMP: {rel:.1e} relative before it, "
+              f"{decades:.1f} decades apart after it; B200 vs serial reference after it: {ours:.1f} decades")
+    assert rel <= 1e-8          # the 1e-8 bar is meaningful where the reference agrees with itself ...
+    assert decades >= 0.5       # ... and it visibly does not beyond ten decades
     A.destroy()
 
 
