@@ -685,6 +685,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
                         "roofline": {"achieved": ka["spmv_dot"]["gbs"], "frac": ka["spmv_dot"]["gbs"] / peak,
                                      "loop_achieved": ka["iteration"]["gbs"], "loop_frac": ka["iteration"]["gbs"] / peak,
                                      "kernels": ka},
+                        "traffic": ncu_traffic("c2"),
                         "check": {"niters": also["niters"], "normr": also["normr"], "x_max_err": also["x_max_err"]}}
         if cpu and isinstance(cpu.get("c2"), dict) and cpu["c2"].get("value"):
             r = cpu["c2"]
@@ -703,7 +704,7 @@ def gpu_arm(args, w: dict, config: dict, rank: int, size: int, local_rank: int):
             "steps": also_pattern["steps"],
             "bytes_per_row_iteration": bytes_per_row_iter(w["stencil"], "pattern", args.eager_x or args.unfused)["iteration"],
             "mirror_bytes": also_pattern["ell_bytes"], "patterns": also_pattern["format"]["patterns"],
-            "kernels": kp, "loop_frac_of_peak": kp["iteration"]["gbs"] / peak,
+            "kernels": kp, "loop_frac_of_peak": kp["iteration"]["gbs"] / peak, "traffic": ncu_traffic("weak512-pattern"),
             "check": {"niters": also_pattern["niters"], "normr": also_pattern["normr"], "x_max_err": also_pattern["x_max_err"]}}
     if also_c3:
         k3 = also_c3["kernels"]

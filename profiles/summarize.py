@@ -74,7 +74,11 @@ def full(tag, workload):
     if p.exists():
         traffic = json.loads(p.read_text())
     for r in rows[2:]:
-        if "spmv_" in r[idx["Kernel Name"]] and ", 1>" in r[idx["Kernel Name"]].split("(")[0]:
+        name = r[idx["Kernel Name"]].split("(")[0]
+        args = [a.strip() for a in name[name.find("<") + 1:name.rfind(">")].split(",")] if "<" in name else []
+        fused_dot = ("spmv_pattern_march_kernel" in name and len(args) > 1 and args[1] == "1") or \
+                    ("spmv_pattern_march_kernel" not in name and "spmv_" in name and args and args[-1] == "1")
+        if fused_dot:
             rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT_TO_BYTES[units[idx["dram__bytes_read.sum"]]]
             wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT_TO_BYTES[units[idx["dram__bytes_write.sum"]]]
             traffic[workload] = rd + wr
