@@ -560,9 +560,14 @@ static int launch_vec_tma_t(hpccg_dev_matrix *m, const VecPtrs &vp, const Finish
 template <class OP>
 static int launch_vec_tma(hpccg_dev_matrix *m, const VecPtrs &vp, const FinishParams &fp, const HaloPut *put, cudaStream_t s) {
   const VecTmaMode &v = vec_tma();
+  // (only the p-producing operation has a put form)
 #define HPCCG_VEC_CASE(T, S)                                                                        \
-  if (v.tile == T && v.stages == S && VecTmaCfg<OP, T, S>::kSmemBytes <= 227 * 1024)                \
-    return put ? launch_vec_tma_t<OP, T, S, true>(m, vp, fp, put, s) : launch_vec_tma_t<OP, T, S, false>(m, vp, fp, put, s);
+  if (v.tile == T && v.stages == S && VecTmaCfg<OP, T, S>::kSmemBytes <= 227 * 1024) {              \
+    if constexpr (OP::kOut == 2) {                                                                  \
+      if (put) return launch_vec_tma_t<OP, T, S, true>(m, vp, fp, put, s);                          \
+    }                                                                                               \
+    return launch_vec_tma_t<OP, T, S, false>(m, vp, fp, nullptr, s);                                \
+  }
   HPCCG_VEC_CASE(1024, 2)
   HPCCG_VEC_CASE(1024, 3)
   HPCCG_VEC_CASE(1024, 4)
@@ -571,7 +576,10 @@ static int launch_vec_tma(hpccg_dev_matrix *m, const VecPtrs &vp, const FinishPa
   HPCCG_VEC_CASE(4096, 2)
 #undef HPCCG_VEC_CASE
   // a shape this operation has no room for: the nearest that fits
-  return put ? launch_vec_tma_t<OP, 1024, 3, true>(m, vp, fp, put, s) : launch_vec_tma_t<OP, 1024, 3, false>(m, vp, fp, put, s);
+  if constexpr (OP::kOut == 2) {
+    if (put) return launch_vec_tma_t<OP, 1024, 3, true>(m, vp, fp, put, s);
+  }
+  return launch_vec_tma_t<OP, 1024, 3, false>(m, vp, fp, nullptr, s);
 }
 
 // Whole-matrix SpMV (+ optional fused x.y) in one launch.

@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "hpccg-sycl_b200" / "lib" / "libhpccg_b200.so"
-WATCH = ["UBLKCP", "SYNCS", "LDG.E.256", "LDG.E.NA.ENL2.256", "STG.E.ENL2.256", "STG.E.256", "LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS",
+WATCH = ["UBLKCP", "UBLKPF", "SYNCS", "UCGABAR", "SHFL", "CCTL", "LDG.E.256", "LDG.E.NA.ENL2.256", "STG.E.ENL2.256", "STG.E.256", "LDG.E.64.STRONG.SYS", "STG.E.64.STRONG.SYS",
          "LDC", "DMUL", "DADD", "DFMA", "HMMA", "UTC"]
 
 

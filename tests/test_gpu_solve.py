@@ -424,3 +424,73 @@ def test_full_size_config2_properties(H, cuda):
         assert abs(out["hist"][0] - 7475.3028032314514) <= 1e-8 * 7475.3028032314514
         assert abs(out["normr"] - 2.2419957139761042e-18) <= 1e-8 * 2.2419957139761042e-18
     A.destroy()
+
+
+def test_compress_invalidates_a_captured_solve(H, refwrap, cuda):
+    """A solve captured as a CUDA graph refers to the SELL arrays; hpccg_dev_matrix_compress releases them, so the graph
+    must go with them (a replay would run the old kernels on freed memory).  After the format switch the same call
+    sequence still gives the reference's history."""
+    torch = cuda
+    H.set_rank(0, 1)
+    H.set_options(27, False)
+    A = H.generate_matrix(48, 48, 24)  # too many rows for the single-kernel solve: graph path
+    m = A.device()
+    n = A.local_nrow
+    b = torch.from_numpy(A.b.copy()).cuda()
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    hists = []
+    for _ in range(3):  # direct, capture + launch, replay
+        x.zero_()
+        hists.append(H.dev.cg_solve(m, b, x, 60, 0.0, flags=H.SOLVE_GRAPH)["hist"])
+    assert np.array_equal(hists[0], hists[2], equal_nan=True)
+    assert m.compress()["format"] == 1
+    for _ in range(3):  # same key as before the switch
+        x.zero_()
+        out = H.dev.cg_solve(m, b, x, 60, 0.0, flags=H.SOLVE_GRAPH)
+        assert out["niters"] == 59
+        rel = np.abs(out["hist"][:60] - hists[0][:60]) / hists[0][:60]
+        assert rel.max() <= 1e-8
+    H.set_options(27, True)
+    A.destroy()
+
+
+def test_localised_matrix_is_not_solved_as_a_single_rank(H, cuda):
+    """A matrix with halo columns solved under a 1-rank context would read a halo nobody fills: refused, not wrong."""
+    torch = cuda
+    mats = _build_ranks(H, (8, 8, 4), 2, 27, True)
+    H.set_rank(0, 1)
+    m = mats[0].device()
+    n = mats[0].local_nrow
+    b = torch.from_numpy(mats[0].b.copy()).cuda()
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    with pytest.raises(H.HpccgError, match="halo columns"):
+        H.dev.cg_solve(m, b, x, 10, 0.0)
+    for A in mats:
+        A.destroy()
+
+
+def test_second_device_gets_its_own_kernel_setup(H, refwrap, cuda):
+    """Occupancy results and the dynamic-shared-memory opt-in of the TMA kernels are per device: a process that moves to
+    a second GPU (hpccg_set_device) must be able to run the 81-166 KB kernels there."""
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hpccg_sycl_b200._capi import lib, check
+    H.set_rank(0, 1)
+    H.set_options(27, True)
+    with refwrap.RefWorld(20, 30, 10, variant=ref_variant()) as R:
+        ref = R.solve(150)
+    try:
+        for dev in (0, 1):
+            check(lib.hpccg_set_device(dev))
+            torch.cuda.set_device(dev)
+            A = H.generate_matrix(20, 30, 10)
+            m = A.device()
+            b = torch.from_numpy(A.b.copy()).to(f"cuda:{dev}")
+            x = torch.zeros(A.local_nrow, dtype=torch.float64, device=f"cuda:{dev}")
+            out = H.dev.cg_solve(m, b, x, 150, 0.0)  # normal loop: TMA SpMV
+            check_history(out["hist"], ref["hist"], out["niters"], ref["niters"])
+            A.destroy()
+    finally:
+        check(lib.hpccg_set_device(0))
+        torch.cuda.set_device(0)
