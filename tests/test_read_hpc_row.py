@@ -178,7 +178,8 @@ def test_power_law_matrix_is_stored_as_sell_c_sigma(H, refwrap, cuda, tmp_path, 
     info = m.info()
     assert m.format()["format"] == 2 and info["slots"] == int(nnz.max())
     stored = int(nnz.sum())
-    assert m.bytes() <= 1.3 * 12 * stored, (m.bytes(), 12 * stored)
+    sorted_bytes = m.bytes()
+    assert sorted_bytes <= 1.3 * 12 * stored, (sorted_bytes, 12 * stored)
     assert 12 * info["slots"] * info["padded_rows"] > 20 * 12 * stored  # what the uniform layout would have taken
     # the canonical view of the mirror is the matrix
     vals, cols = m.download()
@@ -208,7 +209,7 @@ def test_power_law_matrix_is_stored_as_sell_c_sigma(H, refwrap, cuda, tmp_path, 
     monkeypatch.setenv("HPCCG_B200_SIGMA", "1")
     B = H.read_HPC_row(path)
     mb = B.device()
-    assert mb.format()["format"] == 2 and mb.bytes() > m.bytes()
+    assert mb.format()["format"] == 2 and mb.bytes() > 2 * sorted_bytes, (mb.bytes(), sorted_bytes)
     y2 = np.empty(n)
     H.HPC_sparsemv(B, v, y2)
     assert np.array_equal(y2, y)
