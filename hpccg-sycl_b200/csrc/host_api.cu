@@ -110,6 +110,102 @@ bool is_device_pointer(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// ---- pageable caller vectors ---------------------------------------------------------------------------------------------
+// The vectors generate_matrix hands out are page-locked, but a caller may bring its own `new double[]` (what the reference's
+// generate_matrix.cpp:233-235 allocates).  The driver copies pageable memory through small internal bounce buffers at ~13 GB/s;
+// large transfers therefore go through two 64 MB page-locked buffers of this library instead, filled / drained by a few host
+// threads while the previous chunk is on the link (measured: see DESIGN.md section 4, "pageable").
+bool is_page_locked(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+struct PinnedBounce {
+  static constexpr size_t kChunk = 64u << 20;
+  char *buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int ensure() {
+    for (int i = 0; i < 2; ++i) {
+      if (!buf[i]) HPCCG_CUDA(cudaMallocHost(&buf[i], kChunk));
+      if (!ev[i]) HPCCG_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+  }
+  ~PinnedBounce() {
+    for (int i = 0; i < 2; ++i) {
+      if (buf[i]) cudaFreeHost(buf[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+  }
+};
+PinnedBounce &bounce() {
+  static thread_local PinnedBounce b;
+  return b;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  const unsigned nt = std::min<unsigned>(worker_count(), 8u);
+  if (nt <= 1 || bytes < (8u << 20)) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([=] {
+      const size_t lo = bytes * t / nt / 64 * 64, hi = (t + 1 == nt) ? bytes : bytes * (t + 1) / nt / 64 * 64;
+      std::memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo);
+    });
+  for (auto &t : th) t.join();
+}
+
+// host -> device of a (possibly pageable) host range, stream-ordered on `s`; returns when the host range has been read
+int upload(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t s) {
+  if (bytes < (16u << 20) || is_page_locked(src_host) || std::getenv("HPCCG_B200_NO_BOUNCE")) {
+    HPCCG_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  PinnedBounce &b = bounce();
+  HPCCG_TRY(b.ensure());
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += PinnedBounce::kChunk, k ^= 1) {
+    const size_t len = std::min(PinnedBounce::kChunk, bytes - off);
+    HPCCG_CUDA(cudaEventSynchronize(b.ev[k]));  // the copy that last used this buffer has left it
+    parallel_memcpy(b.buf[k], static_cast<const char *>(src_host) + off, len);
+    HPCCG_CUDA(cudaMemcpyAsync(static_cast<char *>(dst_dev) + off, b.buf[k], len, cudaMemcpyHostToDevice, s));
+    HPCCG_CUDA(cudaEventRecord(b.ev[k], s));
+  }
+  return 0;
+}
+
+// device -> host into a (possibly pageable) host range; returns when the host range holds the data
+int download(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t s) {
+  if (bytes < (16u << 20) || is_page_locked(dst_host) || std::getenv("HPCCG_B200_NO_BOUNCE")) {
+    HPCCG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+    HPCCG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  PinnedBounce &b = bounce();
+  HPCCG_TRY(b.ensure());
+  const size_t chunks = (bytes + PinnedBounce::kChunk - 1) / PinnedBounce::kChunk;
+  for (size_t c = 0; c <= chunks; ++c) {
+    if (c < chunks) {  // chunk c onto the link ...
+      const size_t off = c * PinnedBounce::kChunk, len = std::min(PinnedBounce::kChunk, bytes - off);
+      HPCCG_CUDA(cudaMemcpyAsync(b.buf[c & 1], static_cast<const char *>(src_dev) + off, len, cudaMemcpyDeviceToHost, s));
+      HPCCG_CUDA(cudaEventRecord(b.ev[c & 1], s));
+    }
+    if (c > 0) {  // ... while chunk c-1 is drained into the caller's memory
+      const size_t off = (c - 1) * PinnedBounce::kChunk, len = std::min(PinnedBounce::kChunk, bytes - off);
+      HPCCG_CUDA(cudaEventSynchronize(b.ev[(c - 1) & 1]));
+      parallel_memcpy(static_cast<char *>(dst_host) + off, b.buf[(c - 1) & 1], len);
+    }
+  }
+  return 0;
+}
+
 // Thread-local staging buffers for the matrix-free calls (ddot, waxpby, compute_residual) on host pointers.
 struct Staging {
   double *buf[3] = {nullptr, nullptr, nullptr};
@@ -855,19 +951,22 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
   if (!bd || !xd) HPCCG_TRY(ensure_scratch(m, std::max<long long>(m->npad, m->ncol + 2)));
   HPCCG_TRY(ensure_solver_workspace(m, std::max(max_iter, 1), ctx().size));
   // Per-kernel CUDA events cost ~6 API calls per iteration: irrelevant when a kernel runs for 100 us, but 3/4 of the wall
-  // time of a launch-bound solve (20x30x10: 43 -> 12 us per iteration).  Below 2^20 rows a single-rank solve therefore
-  // records only the loop time and splits it over times[1..3] by the kernels' algorithmic byte counts.
-  const bool event_timers = ctx().size > 1 || m->n >= (1 << 20) || std::getenv("HPCCG_B200_TIMERS") != nullptr;
+  // time of a launch-bound solve (20x30x10: 43 -> 12 us per iteration).  Below 2^20 rows a solve therefore records only the
+  // loop time and splits it over times[1..3] by the kernels' algorithmic byte counts; times[4..5] stay 0 there.
+  const bool event_timers = m->n >= (1 << 20) || std::getenv("HPCCG_B200_TIMERS") != nullptr;
   // Host vectors: the copies are ordered so that they overlap the solve where the algorithm allows it.  x goes first (p = x
   // and Ap = A p need only x, HPCCG.cpp:347-349), b follows on the copy stream and is awaited right before r = b - Ap
   // (:352); at the end x comes back in chunks behind the kernel that finishes it.  (The launch-bound graph path keeps the
   // plain sequence: its copies are microseconds.)
   SolveIO io;
   const bool pipelined = event_timers && !std::getenv("HPCCG_B200_SERIAL_COPIES");
+  const size_t vec_bytes = sizeof(double) * (size_t)m->n;
   if (!xd) {
-    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_x, x, sizeof(double) * m->n, cudaMemcpyHostToDevice, nullptr));
+    HPCCG_TRY(upload(m->scratch_x, x, vec_bytes, nullptr));
     dx = m->scratch_x;
-    if (pipelined) io.x_host = x;
+    // the chunked x_fixup + copy-back pipeline writes straight into the caller's x: page-locked memory only (a pageable x
+    // comes back through the bounce buffers after the solve)
+    if (pipelined && (is_page_locked(x) || vec_bytes < (16u << 20))) io.x_host = x;
   }
   if (!bd) {
     cudaStream_t bs = nullptr;
@@ -877,7 +976,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
       HPCCG_CUDA(cudaEventRecord(x_up, nullptr));  // b shares the link with x: start it when x is through
       HPCCG_CUDA(cudaStreamWaitEvent(bs, x_up, 0));
     }
-    HPCCG_CUDA(cudaMemcpyAsync(m->scratch_y, b, sizeof(double) * m->n, cudaMemcpyHostToDevice, bs));
+    HPCCG_TRY(upload(m->scratch_y, b, vec_bytes, bs));
     db = m->scratch_y;
     if (pipelined) {
       HPCCG_CUDA(cudaEventRecord(m->ev_io[0], bs));
@@ -906,7 +1005,7 @@ int HPCCG(HPC_Sparse_Matrix *A, double *const b, double *const x, const int max_
     local_times[2] = loop_s * waxpby_b / tot_b;
     local_times[3] = loop_s * spmv_b / tot_b;
   }
-  if (!xd && !io.x_host) HPCCG_CUDA(cudaMemcpy(x, dx, sizeof(double) * m->n, cudaMemcpyDeviceToHost));
+  if (!xd && !io.x_host) HPCCG_TRY(download(x, dx, vec_bytes, nullptr));
   niters = it;
   normr = nr;
 
