@@ -494,3 +494,24 @@ def test_second_device_gets_its_own_kernel_setup(H, refwrap, cuda):
     finally:
         check(lib.hpccg_set_device(0))
         torch.cuda.set_device(0)
+
+
+def test_pageable_and_page_locked_host_vectors_give_the_same_solve(H, cuda):
+    """HPCCG() with the caller's own pageable vectors (what the reference's `new double[]` are): large transfers go through the
+    library's page-locked bounce buffers in 64 MB chunks (84 MB here: two chunks, the second one partial); same bits as with
+    the page-locked vectors generate_matrix hands out."""
+    H.set_rank(0, 1)
+    H.set_options(27, False)
+    A = H.generate_matrix(256, 256, 160)
+    n = A.local_nrow
+    x1 = A.x  # page-locked (generate_matrix registers what it hands out)
+    x1[:] = 0.0
+    it1, nr1, _, h1 = H.HPCCG(A, A.b, x1, 12, 0.0)
+    bp = np.array(A.b, copy=True)  # pageable copies
+    xp = np.zeros(n)
+    it2, nr2, _, h2 = H.HPCCG(A, bp, xp, 12, 0.0)
+    assert it1 == it2 == 11 and nr1 == nr2
+    assert np.array_equal(h1, h2, equal_nan=True)
+    assert np.array_equal(x1, xp)
+    H.set_options(27, True)
+    A.destroy()
