@@ -318,33 +318,16 @@ spmv_sell_ragged_kernel(const double *__restrict__ vals, const int *__restrict__
     const long long off = __ldg(slice_off + slice) + l;
     double sum = 0.0;
     int j = 0;
-    for (; j + 9 <= ns; j += 9) {  // nine entries' loads in flight (A/B at 27 slots: 4 -> 5700, 9 -> see profiles), summed in order
-      int c[9];
-      double v[9];
+    for (; j + 4 <= ns; j += 4) {  // four entries' loads in flight, summed in order
+      int c[4];
+      double v[4];
 #pragma unroll
-      for (int u = 0; u < 9; ++u) {
-        c[u] = ld_stream_s32(cols + off + (long long)(j + u) * kRaggedRows);
-        v[u] = ld_stream_f64(vals + off + (long long)(j + u) * kRaggedRows);
-      }
-      double xv[9];
-#pragma unroll
-      for (int u = 0; u < 9; ++u) xv[u] = __ldg(x + max(c[u], 0));
-#pragma unroll
-      for (int u = 0; u < 9; ++u) {
-        const double t = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
-        sum = c[u] >= 0 ? t : sum;
-      }
-    }
-    for (; j + 3 <= ns; j += 3) {
-      int c[3];
-      double v[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
+      for (int u = 0; u < 4; ++u) {
         c[u] = ld_stream_s32(cols + off + (long long)(j + u) * kRaggedRows);
         v[u] = ld_stream_f64(vals + off + (long long)(j + u) * kRaggedRows);
       }
 #pragma unroll
-      for (int u = 0; u < 3; ++u)
+      for (int u = 0; u < 4; ++u)
         if (c[u] >= 0) sum = __dadd_rn(sum, __dmul_rn(v[u], __ldg(x + c[u])));
     }
     for (; j < ns; ++j) {

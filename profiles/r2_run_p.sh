@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # roofline point of the ragged SELL-C-sigma kernel: the 27-pt 256^3 matrix forced into format 2 (sigma 8192 and sigma 1) vs the TMA path
 mkdir -p gpurun_out
-for mode in ragged ragged_s1; do
+for mode in tma ragged ragged_s1; do
   unset HPCCG_B200_RAGGED HPCCG_B200_SIGMA
   [ $mode = ragged ] && export HPCCG_B200_RAGGED=1
   [ $mode = ragged_s1 ] && export HPCCG_B200_RAGGED=1 HPCCG_B200_SIGMA=1
