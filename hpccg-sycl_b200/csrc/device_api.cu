@@ -392,41 +392,23 @@ static bool use_march(const hpccg_dev_matrix *m, const double *x) {
   return mode == 1 && m->format == 1 && m->march.ok && aligned32(x);
 }
 
-// HPCCG_B200_MARCH_RING=1: keep the lines of the two older planes in a register ring instead of re-reading them from L1 (A/B:
-// 37 % instead of 61 % of the L1 wavefront peak, but 128 registers are not enough for ring + arithmetic: 1.08 vs 0.88 ms)
-static bool march_ring() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char *e = std::getenv("HPCCG_B200_MARCH_RING");
-    mode = (e && e[0] == '1') ? 1 : 0;
+template <class K>
+static int march_grid(K kern, long long steps, PerDeviceInt &cache) {
+  int per_sm = cache.get();
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cache.set(per_sm);
   }
-  return mode == 1;
+  return (int)std::min<long long>(steps, std::min(per_sm * device_info().sm_count, kMaxPartials / 4));
 }
 
-template <int SLOTS, bool DOT, bool NEG1, bool RING>
-static int march_ctas_per_sm() {
-  static PerDeviceInt cache;
-  int cached = cache.get();
-  if (cached) return cached;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_pattern_march_kernel<SLOTS, DOT, NEG1, RING>, kThreads, 0) != cudaSuccess ||
-      per_sm < 1)
-    per_sm = 1;
-  cache.set(per_sm);
-  return per_sm;
-}
-
-template <int SLOTS, bool DOT, bool NEG1, bool RING>
-static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y, long long x_len, int partial_offset,
-                          const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out) {
+template <int SLOTS, bool DOT, bool NEG1>
+static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y, int partial_offset, const FinishParams &fp,
+                          cudaStream_t s, const SpmvHalo &halo) {
   const MarchGeom &g = m->march;
-  const long long steps = (long long)g.cols_x * g.cols_y * g.nz;
-  const int grid = (int)std::min<long long>(steps, std::min(march_ctas_per_sm<SLOTS, DOT, NEG1, RING>() * device_info().sm_count, kMaxPartials / 4));
-  if (grid_out) {
-    *grid_out = grid;
-    return 0;
-  }
-  spmv_pattern_march_kernel<SLOTS, DOT, NEG1, RING><<<grid, kThreads, 0, s>>>(
+  static PerDeviceInt cache;
+  const int grid = march_grid(spmv_pattern_march_kernel<SLOTS, DOT, NEG1>, (long long)g.cols_x * g.cols_y * g.nz, cache);
+  spmv_pattern_march_kernel<SLOTS, DOT, NEG1><<<grid, kThreads, 0, s>>>(
       m->pat_id, m->pat_mask, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, g, x, y, m->n, m->interior_begin,
       m->interior_end, m->partials, partial_offset, grid, &m->state->counter, fp, halo);
   count_launch();
@@ -434,19 +416,14 @@ static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y,
   return 0;
 }
 
-// whole-matrix launch (the marching kernel has no row-range form); grid_out != nullptr: only report the grid
+// whole-matrix launch (the marching kernels have no row-range form)
 template <bool DOT>
-static int launch_march(const hpccg_dev_matrix *m, const double *x, double *y, long long x_len, int partial_offset,
-                        const FinishParams &fp, cudaStream_t s, const SpmvHalo &halo, int *grid_out = nullptr) {
+static int launch_march(const hpccg_dev_matrix *m, const double *x, double *y, int partial_offset, const FinishParams &fp,
+                        cudaStream_t s, const SpmvHalo &halo) {
   const bool neg1 = m->march.neg1 != 0;
   if (m->slots == 7)
-    return neg1 ? launch_march_t<7, DOT, true, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
-                : launch_march_t<7, DOT, false, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
-  if (march_ring())
-    return neg1 ? launch_march_t<27, DOT, true, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
-                : launch_march_t<27, DOT, false, true>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
-  return neg1 ? launch_march_t<27, DOT, true, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out)
-              : launch_march_t<27, DOT, false, false>(m, x, y, x_len, partial_offset, fp, s, halo, grid_out);
+    return neg1 ? launch_march_t<7, DOT, true>(m, x, y, partial_offset, fp, s, halo) : launch_march_t<7, DOT, false>(m, x, y, partial_offset, fp, s, halo);
+  return neg1 ? launch_march_t<27, DOT, true>(m, x, y, partial_offset, fp, s, halo) : launch_march_t<27, DOT, false>(m, x, y, partial_offset, fp, s, halo);
 }
 
 #define HPCCG_PATTERN_DISPATCH(FN, DOT, ...)             \
@@ -589,8 +566,7 @@ static int spmv_full(const hpccg_dev_matrix *m, const double *x, double *y, bool
   if (use_march(m, x) && aligned32(y)) {
     // the 256-bit loads may start up to 3 elements before the last needed one: ncol % 4 == 0 keeps them inside ncol
     // (checked when the geometry was accepted), the solver's own p is padded anyway
-    const long long x_len = (x == m->p) ? round_up(std::max(m->ncol, 2), 512) : m->ncol;
-    return dot ? launch_march<true>(m, x, y, x_len, 0, fp, s, halo) : launch_march<false>(m, x, y, x_len, 0, fp, s, halo);
+    return dot ? launch_march<true>(m, x, y, 0, fp, s, halo) : launch_march<false>(m, x, y, 0, fp, s, halo);
   }
   if (dot) {
     SpmvPlan pl = plan_spmv<true>(m, 0, m->n);

@@ -76,27 +76,6 @@ __device__ __forceinline__ double ld_f64_nc_if(const double *p, bool pred) {
       : "l"(p), "r"((int)pred));
   return v;
 }
-// conditional loads that leave the destination untouched when `pred` is false (register ring)
-__device__ __forceinline__ void ld_f64x4_nc_keep(double4v &v, const double *p, bool pred) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "setp.ne.b32 q, %5, 0;\n"
-      "@q ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];\n"
-      "}"
-      : "+d"(v.a), "+d"(v.b), "+d"(v.c), "+d"(v.d)
-      : "l"(p), "r"((int)pred));
-}
-__device__ __forceinline__ void ld_f64_nc_keep(double &v, const double *p, bool pred) {
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      "setp.ne.b32 q, %2, 0;\n"
-      "@q ld.global.nc.f64 %0, [%1];\n"
-      "}"
-      : "+d"(v)
-      : "l"(p), "r"((int)pred));
-}
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // per-row table path (same as spmv_pattern_kernel's): entries of pattern `pid` in stored order
@@ -187,78 +166,11 @@ __device__ __forceinline__ void march_rows(const double *__restrict__ x, const P
   }
 }
 
-// 27-point register ring.  While a thread marches along z, the three lines of plane z+1 it loads for step z (stencil lines
-// 6..8) are the lines 3..5 of step z+1 and 0..2 of step z+2: they stay in registers, in a ring of three plane slots whose
-// roles rotate with PHASE (the step loop is unrolled three-fold so the slot of every line is a compile-time register), and a
-// step loads only what `loaded` says is missing -- three 256-bit loads instead of nine in steady state, everything after a
-// column switch.  `loaded` has one bit per stencil line, in role order.
-template <int PHASE, bool NEG1, bool UNIFORM, bool DOT>
-__device__ __forceinline__ void march27_ring_rows(const double *__restrict__ x, const Pattern0 &p0, const MarchGeom &g, int row0,
-                                                  bool valid, unsigned runs, bool lft_on, bool rgt_on, int lane, unsigned &loaded,
-                                                  double4v (&rc)[9], double (&s)[kMarchRows], double (&xc)[kMarchRows]) {
-  constexpr int kDiagRun = 4, kDiag = 13;
-  const bool edge_l = lane == 0, edge_r = lane == 31;
-  const bool edge_lane = (UNIFORM || valid) && ((edge_l && lft_on) || (edge_r && rgt_on));
-  const int edge_off = edge_l ? -1 : kMarchRows;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int slot = ((k / 3 + PHASE) % 3) * 3 + k % 3;
-    const bool on = UNIFORM || ((runs >> k) & 1u);
-    const bool missing = !((loaded >> k) & 1u);
-    ld_f64x4_nc_keep(rc[slot], x + (row0 + g.base[k]), (UNIFORM || valid) && (on || (DOT && k == kDiagRun)) && missing);
-  }
-  loaded |= UNIFORM ? 0x1FFu : (valid ? (runs | (DOT ? (1u << kDiagRun) : 0u)) : 0u);
-  // the x-neighbours beyond the warp's ends are not kept in the ring (registers): lane 0 / lane 31 fetch them per plane, one
-  // plane ahead of the arithmetic; they were brought to L1 by this SM's earlier steps / the prefetch of the new plane
-  double ev[9];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) ev[k] = ld_f64_nc_if(x + (row0 + g.base[k] + edge_off), edge_lane && (UNIFORM || ((runs >> k) & 1u)));
-#pragma unroll
-  for (int i = 0; i < kMarchRows; ++i) s[i] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    if (k % 3 == 0 && k + 3 < 9) {
-#pragma unroll
-      for (int q = k + 3; q < k + 6; ++q)
-        ev[q] = ld_f64_nc_if(x + (row0 + g.base[q] + edge_off), edge_lane && (UNIFORM || ((runs >> q) & 1u)));
-    }
-    const int slot = ((k / 3 + PHASE) % 3) * 3 + k % 3;
-    const int e0 = 3 * k;
-    double4v ck = rc[slot];
-    if (DOT && k == kDiagRun) {
-      xc[0] = ck.a;
-      xc[1] = ck.b;
-      xc[2] = ck.c;
-      xc[3] = ck.d;
-    }
-    if (!UNIFORM && !((runs >> k) & 1u)) ck = double4v{0.0, 0.0, 0.0, 0.0};  // line absent for my rows: +0.0 operands
-    double lft = __shfl_up_sync(0xffffffffu, ck.d, 1);
-    double rgt = __shfl_down_sync(0xffffffffu, ck.a, 1);
-    if (UNIFORM) {
-      lft = edge_l ? ev[k] : lft;
-      rgt = edge_r ? ev[k] : rgt;
-    } else {
-      const bool on = (runs >> k) & 1u;
-      lft = (on && lft_on) ? (edge_l ? ev[k] : lft) : 0.0;
-      rgt = (on && rgt_on) ? (edge_r ? ev[k] : rgt) : 0.0;
-    }
-    const double v0 = p0.value[e0], v1 = p0.value[e0 + 1], v2 = p0.value[e0 + 2];
-    const double xs[6] = {lft, ck.a, ck.b, ck.c, ck.d, rgt};
-#pragma unroll
-    for (int i = 0; i < kMarchRows; ++i) {
-      s[i] = march_term<NEG1, false>(s[i], v0, xs[i]);
-      if (e0 + 1 == kDiag) s[i] = march_term<NEG1, true>(s[i], v1, xs[i + 1]);
-      else s[i] = march_term<NEG1, false>(s[i], v1, xs[i + 1]);
-      s[i] = march_term<NEG1, false>(s[i], v2, xs[i + 2]);
-    }
-  }
-}
-
 // pattern descriptor (pat_mask[id], built by hpccg_dev_matrix_compress): bits 0..8 = stencil lines present, bit 9 = the x-1
 // entries are missing, bit 10 = the x+1 entries are missing; kMaskGeneric = not such a sub-pattern of pattern 0
 constexpr unsigned kDescLm = 1u << 9, kDescRm = 1u << 10;
 
-template <int SLOTS, bool DOT, bool NEG1, bool RING>
+template <int SLOTS, bool DOT, bool NEG1>
 __global__ void __launch_bounds__(kMarchLines * 32, 2)
 spmv_pattern_march_kernel(const unsigned short *__restrict__ pat_id, const unsigned *__restrict__ pat_desc,
                           const double *__restrict__ pat_val, const int *__restrict__ pat_delta,
@@ -300,23 +212,13 @@ spmv_pattern_march_kernel(const unsigned short *__restrict__ pat_id, const unsig
     row0_next = step_row0(col, z, valid_next);
     raw_next = load_ids(row0_next, valid_next);
   }
-  // register ring (RING, 27-pt): three plane slots of three lines; `loaded` = lines held, by role
-  double4v rc[9];
-  unsigned loaded = 0u;
-  int phase = 0;
-  if (RING) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) rc[k] = double4v{0.0, 0.0, 0.0, 0.0};
-  }
   for (long long step = s_begin; step < s_end; ++step) {
     const bool valid = valid_next;
     const int row0 = row0_next;
     const uint2 raw = raw_next;
-    bool wrapped = false;
     if (++z == g.nz) {
       z = 0;
       ++col;
-      wrapped = true;
     }
     if (step + 1 < s_end) {
       row0_next = step_row0(col, z, valid_next);
@@ -354,34 +256,7 @@ spmv_pattern_march_kernel(const unsigned short *__restrict__ pat_id, const unsig
     const bool uniform = __all_sync(0xffffffffu, lane_ok);
     double s[kMarchRows], xc[kMarchRows] = {0.0, 0.0, 0.0, 0.0};
     bool simple = true;
-    if constexpr (RING) {
-      unsigned runs = 0x1FFu;
-      bool lft_on = true, rgt_on = true;
-      if (!uniform) {
-        unsigned d[kMarchRows];
-#pragma unroll
-        for (int i = 0; i < kMarchRows; ++i) d[i] = valid ? __ldg(pat_desc + pid[i]) : kMaskGeneric;
-        runs = d[0] & 0x1FFu;
-        simple = d[1] == runs && d[2] == runs && (d[0] & ~kDescLm) == runs && (d[3] & ~kDescRm) == runs;
-        lft_on = !(d[0] & kDescLm);
-        rgt_on = !(d[3] & kDescRm);
-        const unsigned runs0 = __shfl_sync(0xffffffffu, runs, 0);
-        simple = __all_sync(0xffffffffu, !valid || (simple && runs == runs0));
-        if (!simple) runs = 0u;
-      }
-      if (uniform) {
-        if (phase == 0) march27_ring_rows<0, NEG1, true, DOT>(x, p0, g, row0, true, runs, u_lft, u_rgt, lane, loaded, rc, s, xc);
-        else if (phase == 1) march27_ring_rows<1, NEG1, true, DOT>(x, p0, g, row0, true, runs, u_lft, u_rgt, lane, loaded, rc, s, xc);
-        else march27_ring_rows<2, NEG1, true, DOT>(x, p0, g, row0, true, runs, u_lft, u_rgt, lane, loaded, rc, s, xc);
-      } else {
-        if (phase == 0) march27_ring_rows<0, NEG1, false, DOT>(x, p0, g, row0, valid, runs, lft_on, rgt_on, lane, loaded, rc, s, xc);
-        else if (phase == 1) march27_ring_rows<1, NEG1, false, DOT>(x, p0, g, row0, valid, runs, lft_on, rgt_on, lane, loaded, rc, s, xc);
-        else march27_ring_rows<2, NEG1, false, DOT>(x, p0, g, row0, valid, runs, lft_on, rgt_on, lane, loaded, rc, s, xc);
-      }
-      // the next step is one plane up: roles 3..8 become 0..5 -- or a new column, where nothing of the ring applies
-      phase = phase == 2 ? 0 : phase + 1;
-      loaded = wrapped ? 0u : (loaded >> 3);
-    } else if (uniform) {
+    if (uniform) {
       march_rows<SLOTS, NEG1, true, DOT>(x, p0, g, row0, true, 0u, u_lft, u_rgt, lane, s, xc);
     } else {
       unsigned d[kMarchRows];
