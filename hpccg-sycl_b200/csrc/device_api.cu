@@ -2165,9 +2165,28 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
     HPCCG_TRY(persistent_prepare(m));
     if (m->persist_state == 1) return cg_solve_persistent(m, b, x, max_iter, tolerance, niters, normr, hist_host, loop_ms, (cudaStream_t)stream);
   }
-  if (c.size > 1 || !(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
+  if (!(flags & HPCCG_SOLVE_GRAPH) || (flags & HPCCG_SOLVE_TIMERS))
     return cg_solve_io(m, b, x, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream, nullptr);
+  const bool multi = c.size > 1;
+  if (multi) {
+    // One rank of a multi-GPU job: the peer-memory plane can be captured too -- its exchange stamps and reduction sequence
+    // numbers are device state, the one NCCL call of a solve (the rendezvous gather) is capturable -- the NCCL plane is not
+    // (send / recv on a side stream).  A rank that replays and a rank that launches directly run the same kernels and the
+    // same collective, so ranks need not agree on which of the two they do.
+    if (!nccl_ready() || nccl_size() != c.size || nccl_rank() != c.rank)
+      return fail(HPCCG_ERR_STATE, "hpccg_dev_cg_solve: rank context is %d/%d but no matching NCCL communicator (hpccg_nccl_init)",
+                  c.rank, c.size);
+    bool peer = false;
+    if (!(flags & (HPCCG_SOLVE_NCCL_ONLY | HPCCG_SOLVE_UNFUSED | HPCCG_SOLVE_EAGER_X))) {
+      HPCCG_TRY(ensure_solver_workspace(m, std::max(max_iter, 1), c.size));
+      HPCCG_TRY(peer_link_create(m, m->format == 1 || (m->format == 0 && use_tma_path(m->slots))));
+      peer = m->peer_link != nullptr;
+    }
+    if (!peer)
+      return cg_solve_io(m, b, x, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream, nullptr);
+  }
   std::vector<SolveRank> rk{{m, b, x, c.rank}};
+  const int R = multi ? c.size : 1;
 
   // ---- CUDA-graph replay (launch-bound sizes): the launch sequence of a solve depends only on this key ----
   if (max_iter < 1) max_iter = 1;
@@ -2181,14 +2200,14 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
     m->graph_max_iter = max_iter;
     m->graph_tol = tolerance;
     m->graph_flags = flags;
-    return cg_solve_impl(rk, 1, false, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
+    return cg_solve_impl(rk, R, multi, max_iter, tolerance, niters, normr, hist_host, times, loop_ms, flags, (cudaStream_t)stream);
   }
   if (!m->graph_stream) HPCCG_CUDA(cudaStreamCreateWithFlags(&m->graph_stream, cudaStreamNonBlocking));
   cudaStream_t gs = m->graph_stream;
   if (!m->graph_exec) {
-    HPCCG_TRY(ensure_solver_workspace(m, max_iter, 1));
+    HPCCG_TRY(ensure_solver_workspace(m, max_iter, R));
     HPCCG_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
-    int rc = cg_solve_impl(rk, 1, false, max_iter, tolerance, nullptr, nullptr, nullptr, nullptr, nullptr, flags, gs, true);
+    int rc = cg_solve_impl(rk, R, multi, max_iter, tolerance, nullptr, nullptr, nullptr, nullptr, nullptr, flags, gs, true);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(gs, &graph);
     if (rc) {
@@ -2222,6 +2241,12 @@ int hpccg_dev_cg_solve(hpccg_dev_matrix *m, const double *b, double *x, int max_
   count_launch(3 * (max_iter - 1) + 5);
   HPCCG_CUDA(cudaEventRecord(ev.t1, gs));
   HPCCG_TRY(solve_readback(m, max_iter, niters, normr, hist_host, nullptr, gs));
+  if (multi) {
+    int perr = 0;
+    HPCCG_CUDA(cudaMemcpy(&perr, &m->peer_link->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) return fail(HPCCG_ERR_COMM, "peer-memory wait timed out (%s): a rank of the job did not arrive",
+                          perr == 2 ? "halo" : "scalar reduction");
+  }
   float ms = 0.f;
   HPCCG_CUDA(cudaEventElapsedTime(&ms, ev.t0, ev.t1));
   if (loop_ms) *loop_ms = ms;

@@ -157,8 +157,9 @@ int hpccg_dev_max_abs_diff(int n, const double *v1, const double *v2, double *re
 #define HPCCG_SOLVE_UNFUSED 1   /* literal reference kernel sequence (validation / exact per-kernel times) */
 #define HPCCG_SOLVE_NO_OVERLAP 2 /* halo exchange not overlapped with the interior SpMV */
 #define HPCCG_SOLVE_TIMERS 4    /* record per-kernel CUDA events for times[1..5] */
-#define HPCCG_SOLVE_GRAPH 16    /* single rank, no TIMERS: a repeated solve (same b, x, max_iter, tolerance, flags) is captured once
-                                  * into a CUDA graph and replayed -- for launch-bound sizes; loop_ms then covers the whole solve */
+#define HPCCG_SOLVE_GRAPH 16    /* no TIMERS: a repeated solve (same b, x, max_iter, tolerance, flags) is captured once into a CUDA graph
+                                  * and replayed -- for launch-bound sizes; loop_ms then covers the whole solve.  Single rank, or one
+                                  * rank of a multi-GPU job on the peer-memory plane (ranks need not agree on replaying) */
 #define HPCCG_SOLVE_EAGER_X 32  /* x += alpha p in the kernel right after the SpMV (48 + 24 B/row) instead of deferred into the next
                                   * p-update (24 + 40 B/row, default); same arithmetic, kept for A/B measurements */
 #define HPCCG_SOLVE_PERSISTENT 64 /* single rank, launch-bound sizes (default format, up to ~9600 rows at 27 slots): the WHOLE solve is

@@ -59,6 +59,17 @@ def main():
             worst = check_history(hist, ref["hist"], niters, ref["niters"])
             check_solution(x, ref["x"][rank])
         os.environ["HPCCG_B200_UNFUSED"] = "0"
+        # repeated identical solves: below 2^20 rows HPCCG() captures the second one into a CUDA graph and replays it -- on the
+        # peer-memory plane that works for one rank of a multi-GPU job as well (the NCCL plane keeps launching directly)
+        first = None
+        for rep in range(4):
+            x = A.x.copy()
+            nit, nr, _, hist = H.HPCCG(A, A.b, x, 150, 0.0)
+            check_history(hist, ref["hist"], nit, ref["niters"])
+            check_solution(x, ref["x"][rank])
+            if first is None:
+                first = hist
+            assert np.array_equal(hist, first, equal_nan=True), (comm, fmt, dims, rep)
         # `normr > tolerance` ends the loop at the same iteration on every rank (HPCCG.cpp:358); the kernels enqueued after
         # that return at once on all ranks alike, so nobody is left waiting for a peer
         with refwrap.RefWorld(*dims, size=size, stencil=stencil, variant=variant) as R:
