@@ -147,8 +147,7 @@ __device__ __forceinline__ double peer_allreduce(PeerLink *pl, double local, dou
     const int slot = (int)(seq % kMailSlots);
     Mailbox *dst = pl->box[t];
     *reinterpret_cast<volatile double *>(&dst->value[slot][pl->rank]) = s_local;
-    __threadfence_system();
-    st_release_sys(&dst->seq[slot][pl->rank], seq);
+    st_release_sys(&dst->seq[slot][pl->rank], seq);  // release: the value store above is ordered before the stamp
     Mailbox *own = pl->box[pl->rank];
     double v;
     // once a wait has timed out the job is lost: later waits give up at once, so a dead peer costs one time-out, not one per kernel
