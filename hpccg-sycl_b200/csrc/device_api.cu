@@ -409,7 +409,7 @@ static int launch_march_t(const hpccg_dev_matrix *m, const double *x, double *y,
   static PerDeviceInt cache;
   const int grid = march_grid(spmv_pattern_march_kernel<SLOTS, DOT, NEG1>, (long long)g.cols_x * g.cols_y * g.nz, cache);
   spmv_pattern_march_kernel<SLOTS, DOT, NEG1><<<grid, kThreads, 0, s>>>(
-      m->pat_id, m->pat_mask, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, g, x, y, m->n, m->interior_begin,
+      m->pat_id, m->pat_desc, m->pat_val, m->pat_delta, m->pat_len, m->pattern0, g, x, y, m->n, m->interior_begin,
       m->interior_end, m->partials, partial_offset, grid, &m->state->counter, fp, halo);
   count_launch();
   HPCCG_LAUNCH_CHECK();
@@ -1064,7 +1064,7 @@ int hpccg_dev_matrix_destroy(hpccg_dev_matrix *m) {
   cudaFree(m->pat_val);
   cudaFree(m->pat_delta);
   cudaFree(m->pat_len);
-  cudaFree(m->pat_mask);
+  cudaFree(m->pat_desc);
   cudaFree(m->slice_slots);
   cudaFree(m->slice_off);
   cudaFree(m->perm);
@@ -1281,7 +1281,7 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
   // marching SpMV runs them through the same unrolled code as interior rows: bits 0..8 = lines present, bit 9 = x-1 entries
   // missing, bit 10 = x+1 entries missing.  Anything else (halo rows with remapped columns, perturbed rows, irregular
   // sub-patterns) is marked generic and takes the per-row table path.
-  std::vector<unsigned> h_mask(npat, 0xFFFFFFFFu);
+  std::vector<unsigned> h_desc(npat, 0xFFFFFFFFu);
   {
     const bool s27 = m->slots == 27;
     const int nruns = s27 ? 9 : 5;
@@ -1314,15 +1314,15 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
           rm = r;
         }
       }
-      if (regular) h_mask[id] = runs | (lm == 1 ? (1u << 9) : 0u) | (rm == 1 ? (1u << 10) : 0u);
+      if (regular) h_desc[id] = runs | (lm == 1 ? (1u << 9) : 0u) | (rm == 1 ? (1u << 10) : 0u);
     }
   }
-  unsigned *pat_mask = nullptr;
+  unsigned *pat_desc = nullptr;
   {
-    cudaError_t e_ = cudaMalloc(&pat_mask, sizeof(unsigned) * npat);
-    if (e_ == cudaSuccess) e_ = cudaMemcpy(pat_mask, h_mask.data(), sizeof(unsigned) * npat, cudaMemcpyHostToDevice);
+    cudaError_t e_ = cudaMalloc(&pat_desc, sizeof(unsigned) * npat);
+    if (e_ == cudaSuccess) e_ = cudaMemcpy(pat_desc, h_desc.data(), sizeof(unsigned) * npat, cudaMemcpyHostToDevice);
     if (e_ != cudaSuccess) {
-      cudaFree(pat_mask);
+      cudaFree(pat_desc);
       drop();
       return fail_cuda(e_, "pattern masks", __FILE__, __LINE__);
     }
@@ -1372,7 +1372,7 @@ int hpccg_dev_matrix_compress(hpccg_dev_matrix *m) {
     }
     m->march = g;
   }
-  m->pat_mask = pat_mask;
+  m->pat_desc = pat_desc;
   std::memset(&m->pattern0, 0, sizeof m->pattern0);
   for (int j = 0; j < m->slots; ++j) {
     m->pattern0.value[j] = h_val[j];

@@ -47,8 +47,9 @@ struct hpccg_dev_matrix {
   int *pat_delta = nullptr;
   int *pat_len = nullptr;
   int npat = 0;
-  //   pat_mask  : uint32 [npat]          which entries of pattern 0 the pattern consists of (0xFFFFFFFF: not a sub-pattern)
-  unsigned *pat_mask = nullptr;
+  //   pat_desc  : uint32 [npat]          sub-pattern descriptor relative to pattern 0: stencil lines present, x-1 / x+1 entries
+  //                                      missing (pattern_march.cuh); 0xFFFFFFFF: not such a sub-pattern (per-row table path)
+  unsigned *pat_desc = nullptr;
   hpccg::MarchGeom march{};             // ok: pattern 0 is a 27- / 7-point stencil over x-fastest rows (z-marching SpMV)
   hpccg::Pattern0 pattern0;             // host copy of pattern 0, passed to the SpMV kernel as a __grid_constant__ parameter
 

@@ -26,7 +26,7 @@
 
 namespace hpccg {
 
-constexpr unsigned kMaskGeneric = 0xFFFFFFFFu;  // pattern is not a (regular) sub-pattern of pattern 0
+constexpr unsigned kDescGeneric = 0xFFFFFFFFu;  // pattern is not a (regular) sub-pattern of pattern 0
 constexpr int kMarchLines = 8;                  // y-lines per CTA step = warps per CTA
 constexpr int kMarchRows = 4;                   // x-consecutive rows per thread
 constexpr int kMarchWidth = 32 * kMarchRows;    // x-extent of a column
@@ -166,8 +166,8 @@ __device__ __forceinline__ void march_rows(const double *__restrict__ x, const P
   }
 }
 
-// pattern descriptor (pat_mask[id], built by hpccg_dev_matrix_compress): bits 0..8 = stencil lines present, bit 9 = the x-1
-// entries are missing, bit 10 = the x+1 entries are missing; kMaskGeneric = not such a sub-pattern of pattern 0
+// pattern descriptor (pat_desc[id], built by hpccg_dev_matrix_compress): bits 0..8 = stencil lines present, bit 9 = the x-1
+// entries are missing, bit 10 = the x+1 entries are missing; kDescGeneric = not such a sub-pattern of pattern 0
 constexpr unsigned kDescLm = 1u << 9, kDescRm = 1u << 10;
 
 template <int SLOTS, bool DOT, bool NEG1>
@@ -261,7 +261,7 @@ spmv_pattern_march_kernel(const unsigned short *__restrict__ pat_id, const unsig
     } else {
       unsigned d[kMarchRows];
 #pragma unroll
-      for (int i = 0; i < kMarchRows; ++i) d[i] = valid ? __ldg(pat_desc + pid[i]) : kMaskGeneric;
+      for (int i = 0; i < kMarchRows; ++i) d[i] = valid ? __ldg(pat_desc + pid[i]) : kDescGeneric;
       unsigned runs = d[0] & 0x1FFu;
       simple = d[1] == runs && d[2] == runs && (d[0] & ~kDescLm) == runs && (d[3] & ~kDescRm) == runs;
       const bool lft_on = !(d[0] & kDescLm), rgt_on = !(d[3] & kDescRm);
