@@ -492,12 +492,11 @@ spmv_sell_tma_kernel(const double *__restrict__ vals, const int *__restrict__ co
 #pragma unroll
       for (int j = 0; j < SLOTS; ++j) xv[j] = __ldg(x + max(ci[j], 0));
     } else {
-      // halo entries were written by another GPU during this kernel: read them at L2 (ld.global.cg), never through L1
+      // halo entries were written by another GPU during this kernel and must be read at L2 (ld.global.cg), never through
+      // L1.  The whole stage gathers with ld.cg: choosing the load per entry (ld.cg above n, ldg below) issues BOTH loads
+      // predicated, which made the halo-touching stages -- 3 % of the stages of a 128-plane slab -- twice as expensive
 #pragma unroll
-      for (int j = 0; j < SLOTS; ++j) {
-        const int cj = max(ci[j], 0);
-        xv[j] = cj >= halo.n ? __ldcg(x + cj) : __ldg(x + cj);
-      }
+      for (int j = 0; j < SLOTS; ++j) xv[j] = __ldcg(x + max(ci[j], 0));
     }
     double sum = 0.0;
 #pragma unroll
